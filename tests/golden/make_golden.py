@@ -1,0 +1,225 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by EXECUTING the reference on CPU.
+
+Runs only in the authoring container (needs /root/reference and the installed torchvision CPU ops);
+the GPU box never has /root/reference, it only reads the committed .npz files.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+
+Every array saved here is an input to, or an output of, a reference function (cited per fixture).
+Inputs come from livecell_instance_segmentation_b200.synth with the seeds recorded in the file, so
+large inputs are regenerated from the seed instead of being stored.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from livecell_instance_segmentation_b200 import synth  # noqa: E402
+
+# --- the reference's own code (unmodified, imported from the read-only checkout) ---------------
+from src.components.anchor_generator import AnchorGenerator  # noqa: E402
+from src.utils.box_utils import clip_boxes_to_image, filter_small_boxes, encode_boxes  # noqa: E402
+from src.utils.mask_utils import paste_masks_in_image  # noqa: E402
+from src.utils.proposal_utils import generate_inference_proposals, generate_training_proposals  # noqa: E402
+from torchvision.ops import RoIAlign, nms, MultiScaleRoIAlign  # noqa: E402  (what custom_maskrcnn.py:5 imports)
+from torchvision.ops.poolers import LevelMapper  # noqa: E402
+from torchvision.models.detection._utils import BoxCoder  # noqa: E402
+
+torch.set_num_threads(1)
+T = torch.from_numpy
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}.npz  {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+def ref_topk_indices(obj, k):
+    """The top-k index list the reference computes internally (proposal_utils.py:16-19 / :38-41)."""
+    objectness = torch.sigmoid(T(obj)).permute(1, 2, 0).reshape(-1)
+    s, i = torch.topk(objectness, min(k, objectness.numel()))
+    return s.numpy(), i.numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+def gen_anchors():
+    g = AnchorGenerator()
+    small = g.generate_anchors((5, 7), 4, "cpu").numpy()
+    full = g.generate_anchors((130, 176), 4, "cpu").numpy()          # C1 level-0 map
+    tile = g.generate_anchors((56, 75), 4, "cpu").numpy()            # real 300x222 tiles
+    rows = np.array([0, 1, 8, 9, 1583, 102959, 205919])
+    save("anchors", small=small, full_sha256=sha(full), full_rows=rows, full_vals=full[rows],
+         tile_sha256=sha(tile), sizes=np.array(g.sizes, np.float64), ratios=np.array(g.aspect_ratios, np.float64))
+
+
+def gen_box_utils():
+    rng = np.random.RandomState(7)
+    boxes = rng.uniform(-60, 760, size=(64, 4)).astype(np.float32)
+    clipped = clip_boxes_to_image(T(boxes.copy()), (520, 704)).numpy()
+    keep10 = filter_small_boxes(T(clipped), 10).numpy()
+    keep5 = filter_small_boxes(T(clipped), 5).numpy()
+    anc = synth.make_rois(64, 3)[:, 1:]
+    gt = anc + rng.uniform(-6, 6, size=anc.shape).astype(np.float32)
+    enc = encode_boxes(T(gt), T(anc)).numpy()
+    coder = BoxCoder((1.0, 1.0, 1.0, 1.0))
+    deltas = rng.normal(0, 0.3, size=(64, 4)).astype(np.float32)
+    deltas[0, 2] = 9.0  # exercises the bbox_xform_clip clamp
+    dec = coder.decode_single(T(deltas), T(anc)).numpy()
+    coder2 = BoxCoder((10.0, 10.0, 5.0, 5.0))
+    dec2 = coder2.decode_single(T(deltas), T(anc)).numpy()
+    save("box_utils", boxes=boxes, clipped=clipped, keep10=keep10, keep5=keep5, anchors=anc, gt=gt, encoded=enc,
+         deltas=deltas, decoded_w1=dec, decoded_w10=dec2)
+
+
+def gen_proposals():
+    g = AnchorGenerator()
+    out = {}
+    # small: 96x128 image, 24x32 map
+    obj = synth.make_objectness(2, 9, 24, 32, n_cells=40, seed=11, k=100)
+    anc = g.generate_anchors((24, 32), 4, "cpu")
+    for b in range(2):
+        p, s = generate_inference_proposals(T(obj[b]), anc, (96, 128), "cpu", num_pre_nms=100, score_threshold=0.3,
+                                            nms_threshold=0.4, num_post_nms=30, min_box_size=10)
+        out[f"small_inf_boxes_{b}"], out[f"small_inf_scores_{b}"] = p.numpy(), s.numpy()
+        tp = generate_training_proposals(T(obj[b]), anc, (96, 128), "cpu", num_proposals=120, score_threshold=0.01,
+                                         min_box_size=5)
+        out[f"small_train_boxes_{b}"] = tp.numpy()
+        ts, ti = ref_topk_indices(obj[b], 100)
+        out[f"small_topk_scores_{b}"], out[f"small_topk_index_{b}"] = ts, ti
+    out["small_obj"] = obj
+    # C1: 704x520, reference defaults (250 -> 0.3 -> nms 0.4 -> 50)
+    obj = synth.make_objectness(1, 9, 130, 176, n_cells=150, seed=21, k=250)
+    anc = g.generate_anchors((130, 176), 4, "cpu")
+    p, s = generate_inference_proposals(T(obj[0]), anc, (520, 704), "cpu")
+    ts, ti = ref_topk_indices(obj[0], 250)
+    out.update(c1_seed=np.array(21), c1_inf_boxes=p.numpy(), c1_inf_scores=s.numpy(), c1_topk_index=ti, c1_topk_scores=ts)
+    # C2: 256x256 tile, training defaults (500, 0.01, 5)
+    obj = synth.make_objectness(1, 9, 64, 64, n_cells=20, seed=22, k=500)
+    anc2 = g.generate_anchors((64, 64), 4, "cpu")
+    tp = generate_training_proposals(T(obj[0]), anc2, (256, 256), "cpu")
+    ts, ti = ref_topk_indices(obj[0], 500)
+    out.update(c2_seed=np.array(22), c2_train_boxes=tp.numpy(), c2_topk_index=ti)
+    # C3: crowded, 2000 cells, k=2000, post 1000
+    obj = synth.make_objectness(1, 9, 130, 176, n_cells=2000, seed=23, k=2000)
+    p, s = generate_inference_proposals(T(obj[0]), anc, (520, 704), "cpu", num_pre_nms=2000, num_post_nms=1000)
+    ts, ti = ref_topk_indices(obj[0], 2000)
+    out.update(c3_seed=np.array(23), c3_inf_boxes=p.numpy(), c3_inf_scores=s.numpy(), c3_topk_index=ti)
+    save("proposals", **out)
+
+
+def gen_nms():
+    out = {}
+    rng = np.random.RandomState(5)
+    for n in (250, 2000):
+        r = synth.make_rois(n, 100 + n)[:, 1:]
+        sc = rng.permutation(n).astype(np.float32) / n       # unique scores
+        out[f"boxes_{n}"], out[f"scores_{n}"] = r, sc
+        for thr in (0.4, 0.5, 0.7):
+            out[f"keep_{n}_{int(thr * 10)}"] = nms(T(r), T(sc), thr).numpy()
+    # known-answer probes (SURVEY §8c "oracle facts")
+    b = np.array([[0, 0, 10, 10], [0, 0, 10, 10], [20, 20, 30, 30], [0, 0, 10, 10], [21, 21, 31, 31]], np.float32)
+    s = np.array([0.5, 0.9, 0.7, 0.9, 0.7], np.float32)      # ties -> lower index first
+    out["tie_boxes"], out["tie_scores"], out["tie_keep"] = b, s, nms(T(b), T(s), 0.5).numpy()
+    b = np.array([[0, 0, 10, 10], [0, 0, 4, 10], [0, 0, 10, 5]], np.float32)   # IoU exactly 0.4f and 0.5
+    s = np.array([0.9, 0.8, 0.7], np.float32)
+    out["eq_boxes"], out["eq_scores"] = b, s
+    out["eq_keep_04"], out["eq_keep_05"] = nms(T(b), T(s), 0.4).numpy(), nms(T(b), T(s), 0.5).numpy()
+    b = np.array([[5, 5, 5, 5], [5, 5, 5, 5], [5, 5, 5, 9], [0, 0, 10, 10]], np.float32)   # zero area: NaN IoU
+    s = np.array([0.9, 0.8, 0.7, 0.6], np.float32)
+    out["zero_boxes"], out["zero_scores"], out["zero_keep"] = b, s, nms(T(b), T(s), 0.4).numpy()
+    b = np.array([[0, 0, 10, 10], [1, 1, 11, 11], [50, 50, 60, 60]], np.float32)
+    s = np.array([0.5, np.nan, 0.7], np.float32)             # NaN score sorts first
+    out["nan_boxes"], out["nan_scores"], out["nan_keep"] = b, s, nms(T(b), T(s), 0.4).numpy()
+    save("nms", **out)
+
+
+def gen_roi_align():
+    out = {}
+    feat = synth.make_features(2, 8, 20, 24, seed=31)
+    rois = synth.make_rois(24, 32, img_h=80, img_w=96, batch=2, edge_cases=True)
+    out["feat"], out["rois"] = feat, rois
+    rng = np.random.RandomState(33)
+    for tag, (P, sr, al) in {"p7": (7, 2, False), "p14": (14, 2, False), "p7a": (7, 2, True), "p7ad": (7, 0, False)}.items():
+        op = RoIAlign(output_size=(P, P), spatial_scale=0.25, sampling_ratio=sr, aligned=al)
+        f = T(feat).clone().requires_grad_(True)
+        y = op(f, T(rois))
+        g = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+        y.backward(T(g))
+        out[f"out_{tag}"], out[f"gout_{tag}"], out[f"gin_{tag}"] = y.detach().numpy(), g, f.grad.numpy()
+    # the reference call form: feature_map[b:b+1], [proposals]  (src/custom_maskrcnn.py:177)
+    op = RoIAlign(output_size=(7, 7), spatial_scale=1.0 / 4.0, sampling_ratio=2)
+    out["out_listform"] = op(T(feat[:1]), [T(rois[:, 1:])]).numpy()
+    # multi-level (P2): MultiScaleRoIAlign over 4 levels of a 128x160 image
+    feats = {str(i): T(synth.make_features(1, 8, 32 >> i, 40 >> i, seed=40 + i)) for i in range(4)}
+    boxes = synth.make_rois(40, 41, img_h=128, img_w=160, mode="fpn")[:, 1:]
+    ms = MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+    out["ms_out"] = ms(feats, [T(boxes)], [(128, 160)]).numpy()
+    out["ms_boxes"] = boxes
+    out["ms_levels"] = LevelMapper(2, 5)([T(boxes)]).numpy()
+    big = synth.make_rois(4096, 42, mode="fpn")[:, 1:]
+    out["lm_boxes"], out["lm_levels"] = big, LevelMapper(2, 5)([T(big)]).numpy()
+    save("roi_align", **out)
+
+
+def gen_paste():
+    out = {}
+    probs = synth.make_mask_probs(8, 28, seed=51)
+    boxes = synth.make_det_boxes(8, 52, img_h=64, img_w=80, lo=6, hi=40, edge_cases=True)
+    out["probs"], out["boxes"] = probs, boxes
+    out["masks"] = paste_masks_in_image(T(probs), T(boxes), (64, 80), threshold=0.5).numpy()
+    # full frame 704x520, 12 detections, stored bit-packed (values are {0,255})
+    probs = synth.make_mask_probs(12, 28, seed=53)
+    boxes = synth.make_det_boxes(12, 54)
+    m = paste_masks_in_image(T(probs), T(boxes), (520, 704)).numpy()
+    assert set(np.unique(m)) <= {0, 255}
+    out["full_seed_probs"], out["full_seed_boxes"] = np.array(53), np.array(54)
+    out["full_masks_bits"] = np.packbits(m > 0)
+    save("paste", **out)
+
+
+def gen_pipeline():
+    """Region pipeline chained exactly as forward_inference does (src/custom_maskrcnn.py:164-207),
+    with the PyTorch heads replaced by seeded synthetic scores / mask probabilities."""
+    g = AnchorGenerator()
+    B, h, w, H, W = 2, 24, 32, 96, 128
+    obj = synth.make_objectness(B, 9, h, w, n_cells=60, seed=61, k=200)
+    feat = synth.make_features(B, 16, h, w, seed=62)
+    anc = g.generate_anchors((h, w), 4, "cpu")
+    roi_align = RoIAlign(output_size=(7, 7), spatial_scale=0.25, sampling_ratio=2)
+    out = dict(obj=obj, feat=feat)
+    for b in range(B):
+        props, sc = generate_inference_proposals(T(obj[b]), anc, (H, W), "cpu", num_pre_nms=200, num_post_nms=60)
+        rf = roi_align(T(feat[b:b + 1]), [props])
+        box_scores = T(synth.make_box_scores((60,), 63 + b))[: len(props)]
+        keep_scores = box_scores > 0.4
+        fb, fs = props[keep_scores], box_scores[keep_scores]
+        keep = nms(fb, fs, 0.5)
+        fb, fs = fb[keep], fs[keep]
+        probs = T(synth.make_mask_probs(60, 28, 65 + b))[: len(fb)]
+        masks = paste_masks_in_image(probs, fb, (H, W))
+        out[f"props_{b}"], out[f"prop_scores_{b}"], out[f"roi_feat_{b}"] = props.numpy(), sc.numpy(), rf.numpy()
+        out[f"det_boxes_{b}"], out[f"det_scores_{b}"], out[f"det_masks_{b}"] = fb.numpy(), fs.numpy(), masks.numpy()
+    save("pipeline", **out)
+
+
+if __name__ == "__main__":
+    gen_anchors()
+    gen_box_utils()
+    gen_proposals()
+    gen_nms()
+    gen_roi_align()
+    gen_paste()
+    gen_pipeline()

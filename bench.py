@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — images/s through RPN select -> NMS -> RoIAlign -> detection NMS -> mask paste.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
+
+Workload (BASELINE.json configs[3] with configs[2]'s crowded parameters; the metric "images/sec
+RPN+RoIAlign+mask-paste" is quoted on it): every GPU processes F = 64 synthetic 704x520 frames per
+step (weak scaling: 512 frames on 8 GPUs), 2000 synthetic cells per frame, pre-NMS top-k 2000,
+post-NMS 1000 proposals, 256-channel level-0 FPN map (130x176), 7x7 RoIAlign, box-score filter 0.4 +
+NMS 0.5 into at most 500 detections, 28x28 mask probabilities pasted to uint8 704x520 frames, one
+all-gather of detection records when N > 1.  The PyTorch heads (out of scope) are replaced
+by seeded synthetic box scores / mask probabilities.
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same step through the
+public API starting from pinned HOST buffers (H2D of every input + D2H of the detection records inside
+the timed region).  `roofline`: the dominant kernel (mask paste, 71 % of the algorithmic bytes) timed
+with CUDA events inside the timed steps.  `cpu_baseline` / `--impl reference`: the CPU oracle port
+(oracle/lcr_oracle.c, OpenMP over all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG_H, IMG_W = 520, 704
+FH, FW, A, C = 130, 176, 9, 256
+PRE_NMS, POST_NMS, MAX_DET, M = 2000, 1000, 500, 28
+N_CELLS = 2000
+ANCHOR_CHOICES = [0, 1, 2, 3, 4, 5]      # cells use the size-32/64 anchors (LIVECell cells are 16-76 px)
+METRIC = "images_per_sec_rpn_roialign_maskpaste"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(frames, n_gpus):
+    return {
+        "workload": f"C4/C3 crowded inference: {frames} synthetic 704x520 frames per GPU per step ({frames * n_gpus} total), "
+                    f"{N_CELLS} cells/frame, pre-NMS top-k {PRE_NMS}, post-NMS {POST_NMS}, {C}-ch 130x176 level-0 map, 7x7 RoIAlign, "
+                    f"<= {MAX_DET} detections, 28x28 mask paste to uint8 704x520",
+        "frames_per_gpu": frames,
+        "feature_layout": "NHWC (channels_last)",
+        "parallelism": f"image-sharded x{n_gpus}, one all-gather of detection records",
+        "l2": "per-step working set (~13 GB of masks + features per GPU) >> 126 MB L2: every step streams from HBM",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs (host side, seeded)
+# ------------------------------------------------------------------------------------------------
+def make_host_inputs(frames, seed0):
+    from livecell_instance_segmentation_b200 import synth
+    obj = np.concatenate([synth.make_objectness(1, A, FH, FW, n_cells=N_CELLS, seed=seed0 + i, k=PRE_NMS,
+                                                anchor_choices=ANCHOR_CHOICES) for i in range(frames)])
+    box_scores = synth.make_box_scores((frames, POST_NMS), seed0 + 10_000)
+    return obj, box_scores
+
+
+def make_mask_probs(n, seed):
+    from livecell_instance_segmentation_b200 import synth
+    base = synth.make_mask_probs(512, M, seed)           # 512 distinct maps tiled over the detection slots
+    reps = (n + 511) // 512
+    return np.tile(base, (reps, 1, 1))[:n]
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def cpu_step(orc, base, obj, feat_nchw, box_scores, probs):
+    """One pass of the region path over len(obj) frames on the host (oracle/lcr_oracle.c)."""
+    F = obj.shape[0]
+    boxes, scores, _, counts = orc.rpn_select_batch(obj, base=base, stride=4, k=PRE_NMS, score_thresh=0.3, min_size=10.0,
+                                                    img_h=IMG_H, img_w=IMG_W)
+    keep, kc = orc.nms_batch(boxes, None, counts, 0.4, post_n=POST_NMS)
+    n_det = 0
+    for f in range(F):
+        n = int(kc[f])
+        pb = boxes[f][keep[f, :n]]
+        rois = np.concatenate([np.zeros((n, 1), np.float32), pb], axis=1)
+        orc.roi_align_fwd(feat_nchw[f:f + 1], rois, 7, 7, 0.25, 2, False)
+        k2 = orc.nms(pb, box_scores[f, :n], 0.5, score_thresh=0.4, use_score_thresh=True, post_n=MAX_DET)
+        orc.paste_masks(probs[: len(k2)], pb[k2], IMG_H, IMG_W)
+        n_det += len(k2)
+    return n_det
+
+
+def cpu_baseline(sample_frames, steps, warmup, seed0=0):
+    from oracle import oracle as orc
+    orc.build()
+    from livecell_instance_segmentation_b200 import synth
+    base = orc.base_anchors()
+    obj, box_scores = make_host_inputs(sample_frames, seed0)
+    feat = synth.make_features(sample_frames, C, FH, FW, seed=seed0 + 77)
+    probs = make_mask_probs(MAX_DET, seed0 + 99)
+    for _ in range(warmup):
+        cpu_step(orc, base, obj, feat, box_scores, probs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(orc, base, obj, feat, box_scores, probs)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": sample_frames / dt, "unit": "images/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"{sample_frames} frames/step x {steps} steps of the same workload (oracle/lcr_oracle.c, OpenMP), "
+                      f"{dt * 1e3:.0f} ms/step"}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = 2
+    cb, dt = cpu_baseline(frames, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(frames, 1), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    line["config"]["workload"] = "bounded sample of: " + workload_config(64, 1)["workload"]
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from livecell_instance_segmentation_b200 import _lib, ops
+    from livecell_instance_segmentation_b200.dist import all_gather_detections
+    from livecell_instance_segmentation_b200.pipeline import RegionConfig, RegionPipeline
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the region pipeline has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F = args.frames
+    n_items = F * world
+
+    # ---- inputs: host (pinned) and device copies --------------------------------------------------
+    obj_h, bs_h = make_host_inputs(F, seed0=rank * F)
+    probs_h = make_mask_probs(F * MAX_DET, 99 + rank)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    feat_d = torch.randn((F, FH, FW, C), generator=g, device=dev, dtype=torch.float32).permute(0, 3, 1, 2)  # NHWC memory
+    host = {
+        "obj": torch.from_numpy(obj_h).pin_memory(),
+        "bs": torch.from_numpy(bs_h).pin_memory(),
+        "probs": torch.from_numpy(probs_h).pin_memory(),
+        "feat": torch.empty((F, FH, FW, C), dtype=torch.float32).pin_memory(),
+    }
+    host["feat"].copy_(feat_d.permute(0, 2, 3, 1))
+    obj_d = host["obj"].to(dev)
+    bs_d = host["bs"].to(dev)
+    probs_d = host["probs"].to(dev)
+    masks_d = torch.empty((F * MAX_DET, IMG_H, IMG_W), dtype=torch.uint8, device=dev)
+    pipe = RegionPipeline(RegionConfig(pre_nms_top_n=PRE_NMS, post_nms_top_n=POST_NMS, max_detections=MAX_DET))
+    stream = torch.cuda.current_stream()
+    stage_names = ["rpn_select+nms+gather", "roi_align_fwd", "det_nms+gather", "paste+records"]
+
+    def step(obj, feat, bs, probs, ev=None):
+        if ev is not None:
+            ev[0].record(stream)
+        props = pipe.proposals(obj, (IMG_H, IMG_W))
+        if ev is not None:
+            ev[1].record(stream)
+        roi_feat = pipe.pool(feat, props.rois)
+        if ev is not None:
+            ev[2].record(stream)
+        det = pipe.detections(props, bs)
+        if ev is not None:
+            ev[3].record(stream)
+        det = pipe.paste(det, probs, (IMG_H, IMG_W), out=masks_d)
+        if ev is not None:
+            ev[4].record(stream)
+        rec, cnt = all_gather_detections(det.records, det.counts, n_items) if world > 1 else (det.records, det.counts)
+        return props, roi_feat, det, rec, cnt
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(obj_d, feat_d, bs_d, probs_d)
+    barrier()
+
+    # ---- timed region: inputs resident in HBM ----------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    l0 = _lib.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record(stream)
+    for i in range(args.steps):
+        props, roi_feat, det, rec, cnt = step(obj_d, feat_d, bs_d, probs_d, evs[i])
+    t_end.record(stream)
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms_step = t_start.elapsed_time(t_end) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    value = n_items / (ms_step * 1e-3)
+
+    stage_ms = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(args.steps)])) for j in range(4)]
+    pc = props.counts.cpu().numpy()
+    dc = det.counts.cpu().numpy()
+    n_props, n_det = int(pc.sum()), int(dc.sum())
+
+    # ---- algorithmic bytes ---------------------------------------------------------------
+    bytes_select = F * (4 * A * FH * FW) + F * PRE_NMS * 28 + F * (20 * PRE_NMS + 8 * POST_NMS)
+    bytes_roi = 4 * n_props * C * 49 + F * 4 * C * FH * FW + 20 * F * POST_NMS
+    bytes_det = F * (20 * POST_NMS + 8 * MAX_DET)
+    bytes_paste = n_det * (IMG_H * IMG_W + M * M * 4 + 16) + F * MAX_DET * 24
+    stage_bytes = [bytes_select, bytes_roi, bytes_det, bytes_paste]
+    peak, peak_src = peaks()
+    kernels = {n: {"ms": m, "algorithmic_GB": b / 1e9, "GBps": b / 1e9 / (m * 1e-3), "frac_of_hbm_peak": b / 1e9 / (m * 1e-3) / peak}
+               for n, m, b in zip(stage_names, stage_ms, stage_bytes)}
+
+    # dominant kernel alone (paste_rows16_kernel): events around the single launch, output > L2
+    pe = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    valid = det.valid
+    boxes_flat = det.boxes.reshape(-1, 4)
+    for i in range(args.steps):
+        pe[2 * i].record(stream)
+        ops.paste_masks(probs_d, boxes_flat, IMG_H, IMG_W, 0.5, 255, valid=valid, out=masks_d)
+        pe[2 * i + 1].record(stream)
+    torch.cuda.synchronize()
+    paste_ms = float(np.mean([pe[2 * i].elapsed_time(pe[2 * i + 1]) for i in range(args.steps)]))
+    paste_bytes = n_det * (IMG_H * IMG_W + M * M * 4 + 16)
+    roofline = {"kernel": "paste_rows16_kernel", "bound": "hbm", "achieved": paste_bytes / 1e9 / (paste_ms * 1e-3), "peak": peak,
+                "unit": "GB/s", "frac": paste_bytes / 1e9 / (paste_ms * 1e-3) / peak, "traffic": None,
+                "peak_source": peak_src, "bytes_per_launch": paste_bytes, "ms_per_launch": paste_ms,
+                "share_of_step": stage_ms[3] / max(sum(stage_ms), 1e-9)}
+
+    # NMS latency (BASELINE metric "NMS us"): one 2000-box segment, sorted input, CUDA events
+    cand_boxes, _, _, cand_counts = ops.rpn_select([obj_d[:1]], k=PRE_NMS, img_size=(IMG_H, IMG_W), score_thresh=0.3, min_size=10.0,
+                                                   strides=[4], base=pipe.base)
+    ne = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for _ in range(5):
+        ops.nms_batched(cand_boxes[:, 0], None, 0.4, post_n=POST_NMS, counts=cand_counts[:, 0].contiguous())
+    reps = 50
+    ne[0].record(stream)
+    for _ in range(reps):
+        ops.nms_batched(cand_boxes[:, 0], None, 0.4, post_n=POST_NMS, counts=cand_counts[:, 0].contiguous())
+    ne[1].record(stream)
+    torch.cuda.synchronize()
+    nms_us = ne[0].elapsed_time(ne[1]) * 1e3 / reps
+
+    # ---- e2e: same step from pinned host buffers, H2D + D2H inside the timed region -----------------
+    dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    rec_h = torch.empty((n_items, MAX_DET, 6), dtype=torch.float32).pin_memory()
+    cnt_h = torch.empty((n_items,), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        for k in ("obj", "bs", "probs", "feat"):
+            dbuf[k].copy_(host[k], non_blocking=True)
+        feat = dbuf["feat"].permute(0, 3, 1, 2)
+        _, _, _, rec, cnt = step(dbuf["obj"], feat, dbuf["bs"], dbuf["probs"])
+        rec_h.copy_(rec, non_blocking=True)
+        cnt_h.copy_(cnt, non_blocking=True)
+        stream.synchronize()                       # the caller holds the detections on the host
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = sum(int(v.numel() * v.element_size()) for v in host.values())
+    d2h = int(rec_h.numel() * 4 + cnt_h.numel() * 4)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(F, world), "clocks": clocks,
+            "e2e": {"value": n_items / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "d2h": "detection records + counts (pasted masks stay sharded in HBM, SURVEY §8e)"},
+            "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "nms_us_2000_boxes": nms_us,
+            "proposals_per_frame": n_props / F, "detections_per_frame": n_det / F,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_baseline(2, 3, 1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3          # timing rule: W >= 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 #define LCR_VERSION 100          /* 0.1.0 */
-#define LCR_MAX_ANCHORS 32       /* anchors per location (reference: 9, src/components/anchor_generator.py:11) */
+#define LCR_MAX_ANCHORS 16       /* anchors per location (reference: 9, src/components/anchor_generator.py:11) */
 #define LCR_MAX_LEVELS 8         /* FPN levels per call (reference: 4, src/custom_maskrcnn.py:45) */
 #define LCR_MAX_TOPK 8192        /* pre-NMS top-k capacity per (image, level) segment */
 #define LCR_MAX_NMS_BOXES 32768  /* boxes per NMS segment */
@@ -152,11 +152,13 @@ int lcr_nms_f32(const float* boxes, const float* scores, const int* category, co
 /* Gather helper used between stages: out_boxes[s][j] = boxes[s][keep[s][j]] (and scores likewise)
  * for j < keep_counts[s]; also emits torchvision-format rois [S*post_n, 5] = (batch_idx, box) with
  * batch_idx = image_of_segment_host? : s, and batch_idx = -1 for padding rows j >= keep_counts[s].
- * Any output pointer may be NULL.  (The anchors[keep] / proposals[keep] indexing of
+ * out_valid [S*post_n] u8 = (j < keep_counts[s]) feeds lcr_paste_masks_u8.  Any output pointer may
+ * be NULL.  (The anchors[keep] / proposals[keep] indexing of
  * proposal_utils.py:56-57 and custom_maskrcnn.py:193-195.) */
 int lcr_gather_kept_f32(const float* boxes, const float* scores, const int64_t* keep,
                         const int* keep_counts, int S, int in_stride, int post_n,
-                        float* out_boxes, float* out_scores, float* out_rois, void* stream);
+                        float* out_boxes, float* out_scores, float* out_rois, uint8_t* out_valid,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a11. FPN level assignment.  Replaces LevelMapper.__call__ (TV:ops/poolers.py:73-84):

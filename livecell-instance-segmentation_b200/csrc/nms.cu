@@ -1,0 +1,296 @@
+// nms.cu — batched greedy NMS (a8): stable rank sort -> bitmask IoU build -> warp resolve.
+//
+// Replaces torchvision.ops.nms at src/utils/proposal_utils.py:55 (thr 0.4) and
+// src/custom_maskrcnn.py:192 (thr 0.5).  torchvision's CUDA op is sort + index_select + a 64x64
+// tiled mask kernel + a single-block gather + nonzero (a host sync), per image, in a Python loop;
+// here S segments (images x levels) are processed by three stream-ordered launches with no sync:
+//
+//   1. nms_rank_kernel     stable descending order of the scores by rank counting on 64-bit keys
+//                          (score key << 32 | ~index): exact for any input, no sort network.
+//                          Skipped when the input is already sorted (the rpn_select output).
+//   2. nms_mask_kernel     upper-triangular suppression bitmask.  A CTA owns a 32-row block and a
+//                          span of 32 column words; the column boxes sit in registers, the row
+//                          boxes in shared memory; one __ballot_sync yields a 32-bit mask word, and
+//                          the 32x32 words are staged in shared memory so rows go out as 128-byte
+//                          coalesced stores.  IoU arithmetic is torchvision's: fp32
+//                          inter/(a_i+a_j-inter), compared in double against the threshold.
+//   3. nms_resolve_kernel  one warp per segment walks the boxes in chunks of 32: the chunk's
+//                          32x32 diagonal block is resolved with register shuffles, and the rows of
+//                          the kept boxes are OR-ed into the `removed` bit-vector (shared memory),
+//                          loads for the next chunk being issued before the serial part.
+//                          Stops as soon as post_n boxes are kept.
+//
+// Bound: latency (N <= 2000 boxes, 20 B each) — reported in microseconds, not GB/s.
+#include "common.cuh"
+
+namespace lcr {
+
+constexpr int kRankThreads = 256;
+
+struct NmsWorkspace {
+  float4* sorted_boxes;  // [S][stride]
+  int* order;            // [S][stride]  sorted position -> original index
+  int* sorted_cat;       // [S][stride]  (only when category given)
+  int* n_valid;          // [S]
+  uint32_t* mask;        // [S][stride][nw]
+  int nw;                // mask words per row
+};
+
+static size_t nms_ws_layout(int S, int stride, void* base, NmsWorkspace* ws) {
+  const int nw = (stride + 31) / 32;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = round_up(off + bytes, 256);
+    return o;
+  };
+  const size_t o_boxes = take((size_t)S * stride * sizeof(float4));
+  const size_t o_order = take((size_t)S * stride * sizeof(int));
+  const size_t o_cat = take((size_t)S * stride * sizeof(int));
+  const size_t o_nv = take((size_t)S * sizeof(int));
+  const size_t o_mask = take((size_t)S * stride * nw * sizeof(uint32_t));
+  if (ws) {
+    char* b = static_cast<char*>(base);
+    ws->sorted_boxes = reinterpret_cast<float4*>(b + o_boxes);
+    ws->order = reinterpret_cast<int*>(b + o_order);
+    ws->sorted_cat = reinterpret_cast<int*>(b + o_cat);
+    ws->n_valid = reinterpret_cast<int*>(b + o_nv);
+    ws->mask = reinterpret_cast<uint32_t*>(b + o_mask);
+    ws->nw = nw;
+  }
+  return off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. rank sort.  grid (ceil(stride/256), S).  key = order_key(score) << 32 | (0xFFFFFFFF - i):
+// descending key order == (score desc, index asc) == torch's stable descending sort.
+// scores == NULL: identity order (already sorted), only n_valid / copies are produced.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRankThreads) nms_rank_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                                                                 const int* __restrict__ category,
+                                                                 const int* __restrict__ counts, int stride,
+                                                                 float score_thresh, int use_thresh, NmsWorkspace ws) {
+  __shared__ unsigned long long tile[kRankThreads];
+  const int s = blockIdx.y;
+  const int n = counts ? min(max(counts[s], 0), stride) : stride;
+  const int i = blockIdx.x * kRankThreads + threadIdx.x;
+  const float* sc = scores ? scores + (size_t)s * stride : nullptr;
+
+  auto key_of = [&](int j) -> unsigned long long {
+    if (j >= n) return 0ull;
+    if (!sc) return ((unsigned long long)0xFFFFFFFFu << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)j);
+    const float v = __ldg(sc + j);
+    if (use_thresh && !(v > score_thresh)) return 0ull;  // dropped (src/custom_maskrcnn.py:185)
+    return ((unsigned long long)order_key(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)j);
+  };
+
+  const unsigned long long mine = key_of(i);
+  int rank = 0, nvalid = 0;
+  if (!sc) {  // already sorted: identity order, no counting
+    rank = i;
+    nvalid = n;
+  }
+  for (int t0 = 0; sc && t0 < n; t0 += kRankThreads) {
+    __syncthreads();
+    tile[threadIdx.x] = key_of(t0 + threadIdx.x);
+    __syncthreads();
+    const int lim = min(kRankThreads, n - t0);
+    for (int j = 0; j < lim; ++j) {
+      const unsigned long long k = tile[j];
+      rank += (k > mine) ? 1 : 0;
+      nvalid += (k != 0ull) ? 1 : 0;
+    }
+  }
+  if (mine != 0ull) {
+    const size_t o = (size_t)s * stride + rank;
+    ws.sorted_boxes[o] = __ldg(boxes + (size_t)s * stride + i);
+    ws.order[o] = i;
+    if (category) ws.sorted_cat[o] = __ldg(category + (size_t)s * stride + i);
+  }
+  if (i == 0) ws.n_valid[s] = nvalid;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. mask build.  grid (spans, row_blocks, S), 256 threads = 8 warps.
+// CTA (span sp, row block rb): rows [32rb, 32rb+32), column words [32sp, 32sp+32).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool iou_gt(const float4 a, float area_a, const float4 b, float area_b, double thr) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float width = fmaxf(__fsub_rn(right, left), 0.f), height = fmaxf(__fsub_rn(bottom, top), 0.f);
+  const float inter = __fmul_rn(width, height);
+  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return (double)iou > thr;  // NaN (0/0) compares false: never suppresses
+}
+
+__global__ void __launch_bounds__(256) nms_mask_kernel(int stride, double thr, int use_cat, NmsWorkspace ws) {
+  __shared__ float4 row_box[32];
+  __shared__ float row_area[32];
+  __shared__ int row_cat[32];
+  __shared__ uint32_t words[32][33];
+
+  const int s = blockIdx.z, rb = blockIdx.y, sp = blockIdx.x;
+  const int n = ws.n_valid[s];
+  const int row0 = rb * 32;
+  const int w_lo = sp * 32;
+  // nothing to do for empty row blocks or spans entirely below the diagonal / beyond n
+  if (row0 >= n || w_lo + 31 < rb || w_lo * 32 >= n) return;
+
+  const float4* boxes = ws.sorted_boxes + (size_t)s * stride;
+  const int* cats = ws.sorted_cat + (size_t)s * stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x < 32) {
+    const int r = row0 + threadIdx.x;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < n) b = boxes[r];
+    row_box[threadIdx.x] = b;
+    row_area[threadIdx.x] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    row_cat[threadIdx.x] = (use_cat && r < n) ? cats[r] : 0;
+  }
+  __syncthreads();
+
+  for (int wl = warp; wl < 32; wl += 8) {
+    const int w = w_lo + wl;
+    uint32_t my_word = 0u;  // lane r ends up holding the word of row r
+    if (w >= rb && w * 32 < n) {
+      const int col = w * 32 + lane;
+      const bool col_ok = col < n;
+      float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok) cb = boxes[col];
+      const float carea = __fmul_rn(__fsub_rn(cb.z, cb.x), __fsub_rn(cb.w, cb.y));
+      const int ccat = (use_cat && col_ok) ? cats[col] : 0;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const bool hit = col_ok && (col > row0 + r) && (!use_cat || ccat == row_cat[r]) &&
+                         iou_gt(row_box[r], row_area[r], cb, carea, thr);
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit);
+        if (lane == r) my_word = word;
+      }
+    }
+    words[lane][wl] = my_word;
+  }
+  __syncthreads();
+  // coalesced write-out: warp q writes rows q, q+8, ...; lanes cover 32 consecutive words (128 B)
+  const int nw = ws.nw;
+  for (int r = warp; r < 32; r += 8) {
+    const int row = row0 + r;
+    const int w = w_lo + lane;
+    if (row < n && w < nw) ws.mask[((size_t)s * stride + row) * nw + w] = words[r][lane];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. resolve.  grid S, 32 threads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxWords = LCR_MAX_NMS_BOXES / 32;
+
+__global__ void __launch_bounds__(32) nms_resolve_kernel(int stride, int post_n, NmsWorkspace ws, int64_t* __restrict__ keep,
+                                                         int* __restrict__ keep_counts) {
+  __shared__ uint32_t removed[kMaxWords];
+  const int s = blockIdx.x, lane = threadIdx.x;
+  const int n = ws.n_valid[s];
+  const int nw = ws.nw;
+  const int nchunks = (n + 31) >> 5;
+  const uint32_t* mask = ws.mask + (size_t)s * stride * nw;
+  const int* order = ws.order + (size_t)s * stride;
+  int64_t* out = keep + (size_t)s * post_n;
+
+  for (int w = lane; w < nchunks; w += 32) removed[w] = 0u;
+  int count = 0;
+  uint32_t diag = (nchunks > 0 && lane < n) ? mask[(size_t)lane * nw] : 0u;
+
+  for (int c = 0; c < nchunks && count < post_n; ++c) {
+    __syncwarp();
+    const int row0 = c << 5;
+    // prefetch the next chunk's diagonal word (address is data-independent)
+    const int nrow = row0 + 32 + lane;
+    const uint32_t diag_next = (c + 1 < nchunks && nrow < n) ? mask[(size_t)nrow * nw + (c + 1)] : 0u;
+
+    const int left = n - row0;
+    const uint32_t in_range = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+    uint32_t alive = ~removed[c] & in_range;
+
+    // speculative loads of the first word block of every row that may still be kept
+    const int w0 = c + 1 + lane;
+    uint32_t rows0[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b)
+      rows0[b] = (((alive >> b) & 1u) && w0 < nchunks) ? mask[(size_t)(row0 + b) * nw + w0] : 0u;
+
+    // serial part: greedy over the chunk's 32x32 diagonal block, in registers
+    uint32_t kept = 0u;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const uint32_t d = __shfl_sync(0xFFFFFFFFu, diag, b);
+      if ((alive >> b) & 1u) {
+        kept |= 1u << b;
+        alive &= ~d;
+      }
+    }
+
+    // emit kept boxes of this chunk in order
+    if ((kept >> lane) & 1u) {
+      const int pos = count + __popc(kept & ((1u << lane) - 1u));
+      if (pos < post_n) out[pos] = (int64_t)order[row0 + lane];
+    }
+    count += __popc(kept);
+
+    // propagate the kept rows into `removed`
+    if (w0 < nchunks) {
+      uint32_t acc = 0u;
+#pragma unroll
+      for (int b = 0; b < 32; ++b) acc |= ((kept >> b) & 1u) ? rows0[b] : 0u;
+      removed[w0] |= acc;
+    }
+    for (int w = w0 + 32; w < nchunks; w += 32) {
+      uint32_t acc = 0u;
+#pragma unroll 8
+      for (int b = 0; b < 32; ++b)
+        if ((kept >> b) & 1u) acc |= mask[(size_t)(row0 + b) * nw + w];
+      removed[w] |= acc;
+    }
+    diag = diag_next;
+  }
+  if (lane == 0) keep_counts[s] = min(count, post_n);
+}
+
+}  // namespace lcr
+
+using namespace lcr;
+
+extern "C" size_t lcr_nms_workspace_bytes(int S, int stride) {
+  if (S <= 0 || stride <= 0) return 256;
+  return nms_ws_layout(S, stride, nullptr, nullptr);
+}
+
+extern "C" int lcr_nms_f32(const float* boxes, const float* scores, const int* category, const int* counts, int S, int stride,
+                           double iou_threshold, float score_thresh, int use_score_thresh, int post_n, int64_t* keep,
+                           int* keep_counts, void* workspace, size_t workspace_bytes, void* stream) {
+  LCR_REQUIRE(S >= 0 && stride > 0 && post_n > 0, LCR_ERR_INVALID_ARG);
+  if (S == 0) return LCR_OK;
+  LCR_REQUIRE(boxes && keep && keep_counts, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(stride <= LCR_MAX_NMS_BOXES && S <= 65535, LCR_ERR_CAPACITY);
+  LCR_REQUIRE(aligned_to(boxes, 16), LCR_ERR_ALIGNMENT);
+  LCR_REQUIRE(workspace && aligned_to(workspace, 256) && workspace_bytes >= lcr_nms_workspace_bytes(S, stride),
+              LCR_ERR_WORKSPACE);
+  cudaStream_t st = as_stream(stream);
+  NmsWorkspace ws;
+  nms_ws_layout(S, stride, workspace, &ws);
+
+  dim3 g1((stride + kRankThreads - 1) / kRankThreads, S);
+  nms_rank_kernel<<<g1, kRankThreads, 0, st>>>(reinterpret_cast<const float4*>(boxes), scores, category, counts, stride,
+                                               score_thresh, use_score_thresh, ws);
+  int rc = after_launch();
+  if (rc != LCR_OK) return rc;
+
+  const int row_blocks = (stride + 31) / 32;
+  const int spans = (ws.nw + 31) / 32;
+  dim3 g2(spans, row_blocks, S);
+  nms_mask_kernel<<<g2, 256, 0, st>>>(stride, iou_threshold, category != nullptr, ws);
+  rc = after_launch();
+  if (rc != LCR_OK) return rc;
+
+  nms_resolve_kernel<<<S, 32, 0, st>>>(stride, post_n, ws, keep, keep_counts);
+  return after_launch();
+}

@@ -1,0 +1,646 @@
+// roi_align.cu — RoIAlign forward / backward (a9, a10) and multi-level pooling (a11), one launch.
+//
+// Replaces torchvision::roi_align / _roi_align_backward as called by
+// RoIAlign((7,7), 0.25, sampling_ratio=2) at src/custom_maskrcnn.py:48-50,:120,:177 and, with
+// several levels + roi_level, MultiScaleRoIAlign (TV:ops/poolers.py:147-227).
+// Arithmetic spec: SURVEY.md App. B.1 / B.2 (restated in oracle/lcr_oracle.c).
+//
+// torchvision's kernel is one thread per output element doing 4 samples x 4 scattered 4-byte NCHW
+// loads (16 L1 transactions per 4 output bytes).  The B200 design here:
+//
+//   * NHWC feature maps (channels_last memory): a pixel is one contiguous C*4-byte vector, so a
+//     warp's load is a full coalesced line and lanes map to channels.
+//   * Separable bilinear pooling.  With sampling_ratio 2 the 2P x 2P sample grid of a RoI is a
+//     tensor product, so out = Wy * F_window * Wx^T.  A thread owns VEC channels, walks the
+//     DISTINCT rows of the RoI window once (row cache of two T-vectors), and inside a row loads
+//     every DISTINCT column once (the a[]/b[] slots below): feature bytes read per RoI are the
+//     unique window, not 16 taps per output.  fp32 FMAs are issued as packed FFMA2 (sm_100).
+//   * Output staging: the [channels][P*P] tile of a RoI (50 176 B) is assembled in shared memory
+//     and leaves with ONE TMA bulk store (cp.async.bulk.global.shared::cta, SASS UBLKCP) — the
+//     dominant traffic (the output) is written as full lines by the copy engine.
+//   * Backward is the transpose: the grad_out tile arrives with one TMA bulk load
+//     (cp.async.bulk.shared::cluster.global + mbarrier), a thread accumulates per distinct window
+//     pixel and issues one vector red.global.add per (pixel, channel pair): lanes hit consecutive
+//     channels, so a warp's atomics coalesce into full 256-byte lines at L2.
+//
+// Roofline: HBM.  Algorithmic bytes fwd = 4*K*C*P*P (out) + unique feature bytes + 20*K.
+// Generic kernels (any strides / sampling ratio / pooled size) back every other configuration.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace lcr {
+
+struct LvParam {
+  float* data;
+  int N, H, W;
+  long long sn, sc, sh, sw;
+  float scale;
+};
+
+struct RoiParams {
+  LvParam lv[LCR_MAX_LEVELS];
+  const float* rois;
+  const int* roi_level;
+  int L, C, K, PH, PW, sr, aligned;
+};
+
+// ------------------------------------------------------------------------------------------------
+// RoI geometry, operation-for-operation the oracle's roi_geometry()/make_tap() (no contraction).
+// ------------------------------------------------------------------------------------------------
+struct RoiGeom {
+  float sw, sh, bw, bh;
+  int gw, gh;
+  int b, lvl;
+  bool live;
+};
+
+__device__ __forceinline__ RoiGeom roi_geom(const RoiParams& p, int k) {
+  RoiGeom g;
+  const float* r = p.rois + (size_t)k * 5;
+  const float bf = __ldg(r);
+  g.lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
+  g.b = (int)bf;
+  g.live = (bf >= 0.f) && g.lvl >= 0 && g.lvl < p.L && g.b < p.lv[g.lvl < 0 || g.lvl >= p.L ? 0 : g.lvl].N;
+  const float scale = p.lv[g.live ? g.lvl : 0].scale;
+  const float off = p.aligned ? 0.5f : 0.0f;
+  g.sw = __fsub_rn(__fmul_rn(__ldg(r + 1), scale), off);
+  g.sh = __fsub_rn(__fmul_rn(__ldg(r + 2), scale), off);
+  const float ew = __fsub_rn(__fmul_rn(__ldg(r + 3), scale), off);
+  const float eh = __fsub_rn(__fmul_rn(__ldg(r + 4), scale), off);
+  float rw = __fsub_rn(ew, g.sw), rh = __fsub_rn(eh, g.sh);
+  if (!p.aligned) {
+    rw = fmaxf(rw, 1.0f);
+    rh = fmaxf(rh, 1.0f);
+  }
+  g.bh = __fdiv_rn(rh, (float)p.PH);
+  g.bw = __fdiv_rn(rw, (float)p.PW);
+  g.gh = p.sr > 0 ? p.sr : (int)ceilf(__fdiv_rn(rh, (float)p.PH));
+  g.gw = p.sr > 0 ? p.sr : (int)ceilf(__fdiv_rn(rw, (float)p.PW));
+  return g;
+}
+
+// position of sample i of bin pbin: start + pbin*bin + (i+0.5)*bin/grid
+__device__ __forceinline__ float sample_pos(float start, int pbin, float bin, int i, int grid) {
+  return __fadd_rn(__fadd_rn(start, __fmul_rn((float)pbin, bin)),
+                   __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)grid));
+}
+
+// 1-D half of make_tap(): neighbours lo/hi and weights (w_lo = 1 - frac, w_hi = frac).
+__device__ __forceinline__ bool axis_tap(float pos, int size, int& lo, int& hi, float& w_lo, float& w_hi) {
+  if (pos < -1.0f || pos > (float)size) {
+    lo = hi = 0;
+    w_lo = w_hi = 0.f;
+    return false;
+  }
+  if (pos <= 0.f) pos = 0.f;
+  lo = (int)pos;
+  if (lo >= size - 1) {
+    hi = lo = size - 1;
+    pos = (float)lo;
+  } else {
+    hi = lo + 1;
+  }
+  w_hi = __fsub_rn(pos, (float)lo);
+  w_lo = __fsub_rn(1.0f, w_hi);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic kernels: one thread per output element, arbitrary strides / pooled size / sampling ratio.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) roi_fwd_generic_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out) {
+  const size_t total = (size_t)p.K * p.C * p.PH * p.PW;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int pw = (int)(idx % p.PW);
+    const int ph = (int)((idx / p.PW) % p.PH);
+    const int c = (int)((idx / ((size_t)p.PW * p.PH)) % p.C);
+    const int k = (int)(idx / ((size_t)p.PW * p.PH * p.C));
+    const RoiGeom g = roi_geom(p, k);
+    float acc = 0.f;
+    if (g.live) {
+      const LvParam& lv = p.lv[g.lvl];
+      const float* f = lv.data + (size_t)g.b * lv.sn + (size_t)c * lv.sc;
+      for (int iy = 0; iy < g.gh; ++iy) {
+        int yl, yh;
+        float wyl, wyh;
+        if (!axis_tap(sample_pos(g.sh, ph, g.bh, iy, g.gh), lv.H, yl, yh, wyl, wyh)) continue;
+        for (int ix = 0; ix < g.gw; ++ix) {
+          int xl, xh;
+          float wxl, wxh;
+          if (!axis_tap(sample_pos(g.sw, pw, g.bw, ix, g.gw), lv.W, xl, xh, wxl, wxh)) continue;
+          float v = __fmul_rn(__fmul_rn(wyl, wxl), __ldg(f + yl * lv.sh + xl * lv.sw));
+          v = __fadd_rn(v, __fmul_rn(__fmul_rn(wyl, wxh), __ldg(f + yl * lv.sh + xh * lv.sw)));
+          v = __fadd_rn(v, __fmul_rn(__fmul_rn(wyh, wxl), __ldg(f + yh * lv.sh + xl * lv.sw)));
+          v = __fadd_rn(v, __fmul_rn(__fmul_rn(wyh, wxh), __ldg(f + yh * lv.sh + xh * lv.sw)));
+          acc = __fadd_rn(acc, v);
+        }
+      }
+      const int cnt = g.gh * g.gw;
+      acc = __fdiv_rn(acc, (float)(cnt > 1 ? cnt : 1));
+    }
+    out[idx] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) roi_bwd_generic_kernel(const __grid_constant__ RoiParams p, const float* __restrict__ gout) {
+  const size_t total = (size_t)p.K * p.C * p.PH * p.PW;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int pw = (int)(idx % p.PW);
+    const int ph = (int)((idx / p.PW) % p.PH);
+    const int c = (int)((idx / ((size_t)p.PW * p.PH)) % p.C);
+    const int k = (int)(idx / ((size_t)p.PW * p.PH * p.C));
+    const RoiGeom g = roi_geom(p, k);
+    if (!g.live) continue;
+    const LvParam& lv = p.lv[g.lvl];
+    float* f = lv.data + (size_t)g.b * lv.sn + (size_t)c * lv.sc;
+    const float go = __ldg(gout + idx);
+    const int cnt = g.gh * g.gw;
+    const float count = (float)(cnt > 1 ? cnt : 1);
+    for (int iy = 0; iy < g.gh; ++iy) {
+      int yl, yh;
+      float wyl, wyh;
+      if (!axis_tap(sample_pos(g.sh, ph, g.bh, iy, g.gh), lv.H, yl, yh, wyl, wyh)) continue;
+      for (int ix = 0; ix < g.gw; ++ix) {
+        int xl, xh;
+        float wxl, wxh;
+        if (!axis_tap(sample_pos(g.sw, pw, g.bw, ix, g.gw), lv.W, xl, xh, wxl, wxh)) continue;
+        atomicAdd(f + yl * lv.sh + xl * lv.sw, __fdiv_rn(__fmul_rn(go, __fmul_rn(wyl, wxl)), count));
+        atomicAdd(f + yl * lv.sh + xh * lv.sw, __fdiv_rn(__fmul_rn(go, __fmul_rn(wyl, wxh)), count));
+        atomicAdd(f + yh * lv.sh + xl * lv.sw, __fdiv_rn(__fmul_rn(go, __fmul_rn(wyh, wxl)), count));
+        atomicAdd(f + yh * lv.sh + xh * lv.sw, __fdiv_rn(__fmul_rn(go, __fmul_rn(wyh, wxh)), count));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path (NHWC, sampling_ratio == 2, square P x P).
+// ------------------------------------------------------------------------------------------------
+enum : uint32_t { kSame = 0u, kShift = 1u, kNew = 2u, kModeMask = 3u, kBorder = 4u, kValid = 8u };
+
+struct __align__(16) AxisSample {
+  int off_lo, off_hi;   // element offsets (already multiplied by the axis stride)
+  float w_lo, w_hi;
+};
+
+template <int P>
+struct RoiTables {
+  AxisSample xs[2 * P];
+  AxisSample ys[2 * P];
+  uint32_t xmode[2 * P];
+  uint32_t ymode[2 * P];
+  int lo[2][2 * P];
+  int hi[2][2 * P];
+};
+
+// Threads t < 2P build both axis tables of the current RoI; thread 0 / 1 then derive the
+// SAME / SHIFT / NEW reuse flags (a sequential scan over <= 2P samples).
+template <int P>
+__device__ __forceinline__ void build_tables(RoiTables<P>& tb, const RoiGeom& g, const LvParam& lv, int tid) {
+  if (tid < 2 * P) {
+    int lo, hi;
+    float wl, wh;
+    bool ok = axis_tap(sample_pos(g.sw, tid >> 1, g.bw, tid & 1, 2), lv.W, lo, hi, wl, wh);
+    tb.xs[tid] = AxisSample{(int)(lo * lv.sw), (int)(hi * lv.sw), wl, wh};
+    tb.lo[0][tid] = ok ? lo : -1;
+    tb.hi[0][tid] = hi;
+    ok = axis_tap(sample_pos(g.sh, tid >> 1, g.bh, tid & 1, 2), lv.H, lo, hi, wl, wh);
+    tb.ys[tid] = AxisSample{(int)(lo * lv.sh), (int)(hi * lv.sh), wl, wh};
+    tb.lo[1][tid] = ok ? lo : -1;
+    tb.hi[1][tid] = hi;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    uint32_t* mode = tid == 0 ? tb.xmode : tb.ymode;
+    int c0 = -1, c1 = -1;
+    for (int t = 0; t < 2 * P; ++t) {
+      const int lo = tb.lo[tid][t], hi = tb.hi[tid][t];
+      if (lo < 0) {
+        mode[t] = 0u;  // invalid: contributes nothing, cache state unchanged
+        continue;
+      }
+      uint32_t m = (lo == c0) ? kSame : ((lo == c1) ? kShift : kNew);
+      if (hi == lo) m |= kBorder;
+      mode[t] = m | kValid;
+      c0 = lo;
+      c1 = hi;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+
+// T[pw] = sum over the two x-samples of bin pw of (w_lo * F[row][x_lo] + w_hi * F[row][x_hi]),
+// every distinct column of the row loaded once.  `row` points at this thread's channel pair.
+template <int P>
+__device__ __forceinline__ void pool_row(const RoiTables<P>& tb, const float* __restrict__ row, float2 (&T)[P]) {
+  float2 a[2 * P], b[2 * P];
+  // phase 1: all loads of the row in flight together (predicated off for reused columns)
+#pragma unroll
+  for (int t = 0; t < 2 * P; ++t) {
+    const uint32_t m = tb.xmode[t];
+    const AxisSample s = tb.xs[t];
+    a[t] = make_float2(0.f, 0.f);
+    b[t] = make_float2(0.f, 0.f);
+    if ((m & kValid) && (m & kModeMask) == kNew) a[t] = __ldg(reinterpret_cast<const float2*>(row + s.off_lo));
+    if ((m & kValid) && (m & kModeMask) != kSame && !(m & kBorder)) b[t] = __ldg(reinterpret_cast<const float2*>(row + s.off_hi));
+  }
+  // phase 2: resolve reuse and accumulate
+  float2 pa = make_float2(0.f, 0.f), pb = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int pw = 0; pw < P; ++pw) T[pw] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < 2 * P; ++t) {
+    const uint32_t m = tb.xmode[t];
+    if (m & kValid) {  // warp-uniform
+      const uint32_t mode = m & kModeMask;
+      const AxisSample s = tb.xs[t];
+      if (mode == kNew) pa = a[t];
+      else if (mode == kShift) pa = pb;
+      if (mode != kSame) pb = (m & kBorder) ? pa : b[t];
+      T[t >> 1] = ffma2(splat(s.w_lo), pa, T[t >> 1]);
+      T[t >> 1] = ffma2(splat(s.w_hi), pb, T[t >> 1]);
+    }
+  }
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_smem_to_global(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Forward.  NT threads, each VEC=2 channels: a work item is (roi, channel group of 2*NT channels).
+template <int P, int NT>
+__global__ void __launch_bounds__(NT, 4) roi_fwd_nhwc_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out,
+                                                          int groups) {
+  constexpr int CPB = 2 * NT;
+  constexpr int PP = P * P;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);                                  // [CPB][PP]
+  RoiTables<P>& tb = *reinterpret_cast<RoiTables<P>*>(smem_raw + sizeof(float) * CPB * PP);
+  const int tid = threadIdx.x;
+  const long long items = (long long)p.K * groups;
+
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int k = (int)(item / groups);
+    const int cg = (int)(item - (long long)k * groups);
+    const int c0 = cg * CPB;
+    const int nch = min(CPB, p.C - c0);          // channels of this group (multiple of 4)
+    const RoiGeom g = roi_geom(p, k);
+    const LvParam& lv = p.lv[g.live ? g.lvl : 0];
+    if (g.live) build_tables<P>(tb, g, lv, tid);  // g.live is block-uniform
+
+    // the previous item's bulk store must have finished READING the tile before it is rewritten
+    if (tid == 0) bulk_wait_read_all();
+    __syncthreads();
+
+    const int c = c0 + 2 * tid;
+    if (2 * tid < nch) {
+      float* my = tile + (size_t)(2 * tid) * PP;
+      if (!g.live) {
+#pragma unroll 7
+        for (int j = 0; j < PP; ++j) {
+          my[j] = 0.f;
+          my[PP + j] = 0.f;
+        }
+      } else {
+        const float* fb = lv.data + (size_t)g.b * lv.sn + c;  // sc == 1
+        float2 T0[P], T1[P];
+#pragma unroll
+        for (int pw = 0; pw < P; ++pw) T0[pw] = T1[pw] = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int ph = 0; ph < P; ++ph) {
+          float2 acc[P];
+#pragma unroll
+          for (int pw = 0; pw < P; ++pw) acc[pw] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t m = tb.ymode[2 * ph + i];
+            if (m & kValid) {  // block-uniform
+              const uint32_t mode = m & kModeMask;
+              const AxisSample s = tb.ys[2 * ph + i];
+              if (mode == kShift) {
+#pragma unroll
+                for (int pw = 0; pw < P; ++pw) T0[pw] = T1[pw];
+              } else if (mode == kNew) {
+                pool_row<P>(tb, fb + s.off_lo, T0);
+              }
+              if (mode != kSame) {
+                if (m & kBorder) {
+#pragma unroll
+                  for (int pw = 0; pw < P; ++pw) T1[pw] = T0[pw];
+                } else {
+                  pool_row<P>(tb, fb + s.off_hi, T1);
+                }
+              }
+#pragma unroll
+              for (int pw = 0; pw < P; ++pw) {
+                acc[pw] = ffma2(splat(s.w_lo), T0[pw], acc[pw]);
+                acc[pw] = ffma2(splat(s.w_hi), T1[pw], acc[pw]);
+              }
+            }
+          }
+          // count = 4 for sampling_ratio 2: multiply by 0.25 is exact
+#pragma unroll
+          for (int pw = 0; pw < P; ++pw) {
+            my[ph * P + pw] = acc[pw].x * 0.25f;
+            my[PP + ph * P + pw] = acc[pw].y * 0.25f;
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_store_smem_to_global(out + ((size_t)k * p.C + c0) * PP, tile, (uint32_t)(nch * PP * sizeof(float)));
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+}
+
+// ---- backward -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_global_to_smem(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(sdst)),
+               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+// Scatter one window row: for the row's distinct columns accumulate sum_t w * U[t>>1] and issue one
+// vector atomic per (column, channel pair).
+template <int P>
+__device__ __forceinline__ void scatter_row(const RoiTables<P>& tb, float* __restrict__ row, const float2 (&U)[P]) {
+  float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+  int o0 = -1, o1 = -1;  // element offsets of the two live columns (-1: empty)
+#pragma unroll
+  for (int t = 0; t < 2 * P; ++t) {
+    const uint32_t m = tb.xmode[t];
+    if (m & kValid) {
+      const uint32_t mode = m & kModeMask;
+      const AxisSample s = tb.xs[t];
+      if (mode == kShift) {
+        if (o0 >= 0) atomicAdd(reinterpret_cast<float2*>(row + o0), a0);
+        a0 = a1; o0 = o1;
+        a1 = make_float2(0.f, 0.f); o1 = -1;
+      } else if (mode == kNew) {
+        if (o0 >= 0) atomicAdd(reinterpret_cast<float2*>(row + o0), a0);
+        if (o1 >= 0) atomicAdd(reinterpret_cast<float2*>(row + o1), a1);
+        a0 = a1 = make_float2(0.f, 0.f);
+        o1 = -1;
+      }
+      o0 = s.off_lo;
+      a0 = ffma2(splat(s.w_lo), U[t >> 1], a0);
+      if (m & kBorder) {
+        a0 = ffma2(splat(s.w_hi), U[t >> 1], a0);
+      } else {
+        o1 = s.off_hi;
+        a1 = ffma2(splat(s.w_hi), U[t >> 1], a1);
+      }
+    }
+  }
+  if (o0 >= 0) atomicAdd(reinterpret_cast<float2*>(row + o0), a0);
+  if (o1 >= 0) atomicAdd(reinterpret_cast<float2*>(row + o1), a1);
+}
+
+template <int P, int NT>
+__global__ void __launch_bounds__(NT, 4) roi_bwd_nhwc_kernel(const __grid_constant__ RoiParams p, const float* __restrict__ gout,
+                                                          int groups) {
+  constexpr int CPB = 2 * NT;
+  constexpr int PP = P * P;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);  // grad_out tile [CPB][PP]
+  RoiTables<P>& tb = *reinterpret_cast<RoiTables<P>*>(smem_raw + sizeof(float) * CPB * PP);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * CPB * PP + sizeof(RoiTables<P>));
+  const int tid = threadIdx.x;
+  const long long items = (long long)p.K * groups;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int k = (int)(item / groups);
+    const int cg = (int)(item - (long long)k * groups);
+    const int c0 = cg * CPB;
+    const int nch = min(CPB, p.C - c0);
+    const RoiGeom g = roi_geom(p, k);
+    if (!g.live) continue;  // block-uniform
+    const LvParam& lv = p.lv[g.lvl];
+    fence_proxy_async_smem();  // generic-proxy reads of the old tile are ordered before the async-proxy refill
+    __syncthreads();           // everyone is done with the previous tile and tables
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)(nch * PP * sizeof(float));
+      mbar_expect_tx(bar, bytes);
+      bulk_load_global_to_smem(tile, gout + ((size_t)k * p.C + c0) * PP, bytes, bar);
+    }
+    build_tables<P>(tb, g, lv, tid);
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+
+    const int c = c0 + 2 * tid;
+    if (2 * tid < nch) {
+      const float* my = tile + (size_t)(2 * tid) * PP;
+      float* fb = lv.data + (size_t)g.b * lv.sn + c;
+      float2 U0[P], U1[P];
+      int r0 = -1, r1 = -1;  // element offsets of the two live rows
+#pragma unroll
+      for (int pw = 0; pw < P; ++pw) U0[pw] = U1[pw] = make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int ph = 0; ph < P; ++ph) {
+        float2 gq[P];  // grad_out[ph][:] / count  (count = 4, exact)
+#pragma unroll
+        for (int pw = 0; pw < P; ++pw) gq[pw] = make_float2(my[ph * P + pw] * 0.25f, my[PP + ph * P + pw] * 0.25f);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t m = tb.ymode[2 * ph + i];
+          if (m & kValid) {
+            const uint32_t mode = m & kModeMask;
+            const AxisSample s = tb.ys[2 * ph + i];
+            if (mode == kShift) {
+              if (r0 >= 0) scatter_row<P>(tb, fb + r0, U0);
+#pragma unroll
+              for (int pw = 0; pw < P; ++pw) {
+                U0[pw] = U1[pw];
+                U1[pw] = make_float2(0.f, 0.f);
+              }
+              r0 = r1;
+              r1 = -1;
+            } else if (mode == kNew) {
+              if (r0 >= 0) scatter_row<P>(tb, fb + r0, U0);
+              if (r1 >= 0) scatter_row<P>(tb, fb + r1, U1);
+#pragma unroll
+              for (int pw = 0; pw < P; ++pw) U0[pw] = U1[pw] = make_float2(0.f, 0.f);
+              r1 = -1;
+            }
+            r0 = s.off_lo;
+            if (m & kBorder) {
+#pragma unroll
+              for (int pw = 0; pw < P; ++pw) {
+                U0[pw] = ffma2(splat(s.w_lo), gq[pw], U0[pw]);
+                U0[pw] = ffma2(splat(s.w_hi), gq[pw], U0[pw]);
+              }
+            } else {
+              r1 = s.off_hi;
+#pragma unroll
+              for (int pw = 0; pw < P; ++pw) {
+                U0[pw] = ffma2(splat(s.w_lo), gq[pw], U0[pw]);
+                U1[pw] = ffma2(splat(s.w_hi), gq[pw], U1[pw]);
+              }
+            }
+          }
+        }
+      }
+      if (r0 >= 0) scatter_row<P>(tb, fb + r0, U0);
+      if (r1 >= 0) scatter_row<P>(tb, fb + r1, U1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int fill_params(RoiParams& p, const LcrFeatLevel* lv, int L, int C, const float* rois, const int* roi_level, int K,
+                       int PH, int PW, int sr, int aligned) {
+  LCR_REQUIRE(lv && L > 0 && C > 0 && K >= 0 && PH > 0 && PW > 0 && sr >= 0, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(L <= LCR_MAX_LEVELS, LCR_ERR_CAPACITY);
+  LCR_REQUIRE(K == 0 || rois, LCR_ERR_INVALID_ARG);
+  for (int l = 0; l < L; ++l) {
+    LCR_REQUIRE(lv[l].data && lv[l].N > 0 && lv[l].H > 0 && lv[l].W > 0, LCR_ERR_INVALID_ARG);
+    p.lv[l] = LvParam{lv[l].data, lv[l].N, lv[l].H, lv[l].W, lv[l].sn, lv[l].sc, lv[l].sh, lv[l].sw, lv[l].spatial_scale};
+  }
+  p.rois = rois;
+  p.roi_level = roi_level;
+  p.L = L; p.C = C; p.K = K; p.PH = PH; p.PW = PW; p.sr = sr; p.aligned = aligned;
+  return LCR_OK;
+}
+
+// NHWC fast path eligibility: sampling_ratio 2, P in {7, 14}, channel stride 1, 8-byte aligned
+// channel pairs, offsets that fit int32, C % 4 == 0 (16-byte bulk-copy granularity of the tile).
+static bool fast_eligible(const RoiParams& p, const void* out) {
+  if (p.sr != 2 || p.PH != p.PW || (p.PH != 7 && p.PH != 14)) return false;
+  if (p.C % 4 != 0 || !aligned_to(out, 16)) return false;
+  for (int l = 0; l < p.L; ++l) {
+    const LvParam& v = p.lv[l];
+    if (v.sc != 1 || v.sw % 2 || v.sh % 2 || v.sn % 2 || !aligned_to(v.data, 8)) return false;
+    if ((long long)v.H * v.sh >= (1ll << 31) || (long long)v.W * v.sw >= (1ll << 31)) return false;
+  }
+  return true;
+}
+
+template <int P, int NT>
+static size_t fast_smem_bytes() {
+  return sizeof(float) * 2 * NT * P * P + sizeof(RoiTables<P>) + 16;
+}
+
+template <int P, int NT, bool BWD>
+static int launch_fast(const RoiParams& p, float* out_or_gout, cudaStream_t st) {
+  const int groups = (p.C + 2 * NT - 1) / (2 * NT);
+  const size_t smem = fast_smem_bytes<P, NT>();
+  const long long items = (long long)p.K * groups;
+  const int per_sm = (int)((227 * 1024) / (smem + 1024));
+  const long long max_blocks = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
+  const int blocks = (int)(items < max_blocks ? items : max_blocks);
+  static thread_local int configured_dev = -1;  // opt in to > 48 KB dynamic shared memory once per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (BWD) {
+    auto kern = roi_bwd_nhwc_kernel<P, NT>;
+    if (configured_dev != dev) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_status(e);
+      configured_dev = dev;
+    }
+    kern<<<blocks, NT, smem, st>>>(p, out_or_gout, groups);
+  } else {
+    auto kern = roi_fwd_nhwc_kernel<P, NT>;
+    if (configured_dev != dev) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_status(e);
+      configured_dev = dev;
+    }
+    kern<<<blocks, NT, smem, st>>>(p, out_or_gout, groups);
+  }
+  return after_launch();
+}
+
+}  // namespace lcr
+
+using namespace lcr;
+
+extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int C, const float* rois, const int* roi_level,
+                                     int K, int PH, int PW, int sampling_ratio, int aligned, float* out, void* stream) {
+  RoiParams p{};
+  int rc = fill_params(p, levels_host, L, C, rois, roi_level, K, PH, PW, sampling_ratio, aligned);
+  if (rc != LCR_OK) return rc;
+  if (K == 0) return LCR_OK;
+  LCR_REQUIRE(out, LCR_ERR_INVALID_ARG);
+  cudaStream_t st = as_stream(stream);
+  if (fast_eligible(p, out)) {
+    if (PH == 7) return launch_fast<7, 128, false>(p, out, st);
+    return launch_fast<14, 32, false>(p, out, st);
+  }
+  const size_t total = (size_t)K * C * PH * PW;
+  const size_t want = (total + 255) / 256;
+  const size_t cap = (size_t)sm_count() * 32;
+  roi_fwd_generic_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(p, out);
+  return after_launch();
+}
+
+extern "C" int lcr_roi_align_bwd_f32(const float* grad_out, const LcrFeatLevel* grad_levels_host, int L, int C, const float* rois,
+                                     const int* roi_level, int K, int PH, int PW, int sampling_ratio, int aligned,
+                                     int zero_grad, void* stream) {
+  RoiParams p{};
+  int rc = fill_params(p, grad_levels_host, L, C, rois, roi_level, K, PH, PW, sampling_ratio, aligned);
+  if (rc != LCR_OK) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (zero_grad) {
+    for (int l = 0; l < L; ++l) {
+      // dense levels only (NCHW or NHWC contiguous): the byte extent is N*C*H*W floats
+      const LvParam& v = p.lv[l];
+      cudaError_t e = cudaMemsetAsync(v.data, 0, sizeof(float) * (size_t)v.N * C * v.H * v.W, st);
+      if (e != cudaSuccess) return cuda_status(e);
+    }
+  }
+  if (K == 0) return LCR_OK;
+  LCR_REQUIRE(grad_out, LCR_ERR_INVALID_ARG);
+  if (fast_eligible(p, grad_out)) {
+    if (PH == 7) return launch_fast<7, 128, true>(p, const_cast<float*>(grad_out), st);
+    return launch_fast<14, 32, true>(p, const_cast<float*>(grad_out), st);
+  }
+  const size_t total = (size_t)K * C * PH * PW;
+  const size_t want = (total + 255) / 256;
+  const size_t cap = (size_t)sm_count() * 32;
+  roi_bwd_generic_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(p, grad_out);
+  return after_launch();
+}

@@ -1,0 +1,360 @@
+"""Tensor-level wrappers over the C-ABI (include/lcr.h): torch is used for device memory and the
+current stream only.  Every function launches hand-written sm_100a kernels from csrc/liblcr.so on
+``torch.cuda.current_stream()``; none of them synchronises.  CPU tensors are rejected loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import LcrFeatLevel, LcrRpnCfg, LcrRpnLevel, check
+
+XFORM_CLIP = math.log(1000.0 / 16)
+
+_workspaces: dict = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.LcrError("liblcr ops need CUDA tensors: the region pipeline has no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Per (device, stream) scratch buffer, grown on demand; owned by the caller side of the ABI."""
+    key = (torch.device(device).index, _stream())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def base_anchors(sizes=(32, 64, 128), aspect_ratios=(0.5, 1.0, 2.0)):
+    """Base anchors in float64 then fp32 — src/components/anchor_generator.py:15-27."""
+    rows = []
+    for size in sizes:
+        for ratio in aspect_ratios:
+            area = size * size
+            h = math.sqrt(area / ratio)
+            w = h * ratio
+            rows.append([-w / 2, -h / 2, w / 2, h / 2])
+    return torch.tensor(rows, dtype=torch.float64).to(torch.float32)
+
+
+def _base_array(base) -> "C.Array":
+    flat = [float(v) for v in torch.as_tensor(base, dtype=torch.float32).reshape(-1).tolist()]
+    if len(flat) > _lib.LCR_MAX_ANCHORS * 4 or len(flat) % 4:
+        raise _lib.LcrError("base anchors: at most %d anchors of 4 floats" % _lib.LCR_MAX_ANCHORS)
+    return (C.c_float * len(flat))(*flat)
+
+
+# ------------------------------------------------------------------------------------------------
+def anchors(h: int, w: int, stride: int, base, device) -> torch.Tensor:
+    """a1 — AnchorGenerator.generate_anchors (src/components/anchor_generator.py:13-37)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.LcrError("liblcr ops need a CUDA device: the region pipeline has no CPU fallback")
+    arr = _base_array(base)
+    A = len(arr) // 4
+    out = torch.empty((h * w * A, 4), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(_lib.load().lcr_anchors_f32(out.data_ptr(), h, w, stride, arr, A, _stream()), "anchors")
+    return out
+
+
+def clip_boxes_(boxes: torch.Tensor, img_h: float, img_w: float) -> torch.Tensor:
+    """a5 — clip_boxes_to_image, in place (src/utils/box_utils.py:32-37)."""
+    _need_cuda(boxes)
+    if boxes.numel() == 0:
+        return boxes
+    if boxes.dtype != torch.float32 or not boxes.is_contiguous():
+        tmp = _f32c(boxes)
+        clip_boxes_(tmp, img_h, img_w)
+        boxes.copy_(tmp)
+        return boxes
+    with torch.cuda.device(boxes.device):
+        check(_lib.load().lcr_clip_boxes_f32(boxes.data_ptr(), boxes.shape[0], float(img_h), float(img_w), _stream()), "clip")
+    return boxes
+
+
+def filter_small_boxes(boxes: torch.Tensor, min_size: float) -> torch.Tensor:
+    """a6 — filter_small_boxes (src/utils/box_utils.py:39-44) -> bool[K]."""
+    _need_cuda(boxes)
+    b = _f32c(boxes)
+    keep = torch.empty((b.shape[0],), dtype=torch.uint8, device=b.device)
+    if b.shape[0]:
+        with torch.cuda.device(b.device):
+            check(_lib.load().lcr_filter_small_boxes_f32(b.data_ptr(), b.shape[0], float(min_size), keep.data_ptr(), _stream()),
+                  "filter_small_boxes")
+    return keep.view(torch.bool)
+
+
+def box_decode(deltas: torch.Tensor, anc: torch.Tensor, weights=(1.0, 1.0, 1.0, 1.0), xform_clip: float = XFORM_CLIP,
+               img_size=None) -> torch.Tensor:
+    """a7 — BoxCoder.decode_single (TV:models/detection/_utils.py:183-224), optional clip."""
+    _need_cuda(deltas, anc)
+    d, a = _f32c(deltas).reshape(-1, 4), _f32c(anc).reshape(-1, 4)
+    out = torch.empty_like(a)
+    w = (C.c_float * 4)(*[float(v) for v in weights])
+    ih, iw = (0.0, 0.0) if img_size is None else (float(img_size[0]), float(img_size[1]))
+    if a.shape[0]:
+        with torch.cuda.device(a.device):
+            check(_lib.load().lcr_box_decode_f32(d.data_ptr(), a.data_ptr(), a.shape[0], w, float(xform_clip), ih, iw,
+                                                 out.data_ptr(), _stream()), "box_decode")
+    return out
+
+
+def rpn_select(objectness: Sequence[torch.Tensor], *, k: int, img_size, score_thresh: float, min_size: float,
+               strides: Optional[Sequence[int]] = None, base=None, anchors_per_level: Optional[Sequence[torch.Tensor]] = None,
+               deltas: Optional[Sequence[torch.Tensor]] = None, score_strict: bool = True, topk_on_sigmoid: bool = True,
+               decode_weights=(1.0, 1.0, 1.0, 1.0), xform_clip: float = XFORM_CLIP):
+    """a2/a3/a12 — batched proposal selection (see lcr_rpn_select_f32 in include/lcr.h).
+
+    objectness: list over levels of [B, A, h, w] logits.  Boxes come from `anchors_per_level`
+    ([h*w*A, 4] tensors) or are generated from `base` (one [A,4] table, or one per level) + `strides`.
+    Returns boxes [B, L, k, 4], scores [B, L, k], index [B, L, k] (i64), counts [B, L] (i32)."""
+    L = len(objectness)
+    objs = [_f32c(o) for o in objectness]
+    _need_cuda(*objs)
+    B, A = objs[0].shape[0], objs[0].shape[1]
+    dev = objs[0].device
+    dls = [None] * L if deltas is None else [_f32c(d) for d in deltas]
+    ancs = [None] * L if anchors_per_level is None else [_f32c(a) for a in anchors_per_level]
+    _need_cuda(*[t for t in dls + ancs if t is not None])
+    levels = (LcrRpnLevel * L)()
+    for l in range(L):
+        lv = levels[l]
+        lv.objectness, lv.deltas, lv.anchors = _ptr(objs[l]), _ptr(dls[l]), _ptr(ancs[l])
+        lv.h, lv.w = objs[l].shape[2], objs[l].shape[3]
+        lv.stride = int(strides[l]) if strides is not None else 0
+        if ancs[l] is None:
+            if base is None or strides is None:
+                raise _lib.LcrError("rpn_select: give anchors_per_level, or base + strides")
+            bl = base[l] if isinstance(base, (list, tuple)) else base
+            arr = _base_array(bl)
+            if len(arr) != A * 4:
+                raise _lib.LcrError("rpn_select: base anchors do not match the objectness channel count")
+            for i, v in enumerate(arr):
+                lv.base_anchors[i] = v
+        elif ancs[l].shape[0] != A * lv.h * lv.w:
+            raise _lib.LcrError("rpn_select: anchors tensor does not match the objectness map")
+    cfg = LcrRpnCfg()
+    cfg.num_anchors, cfg.pre_nms_top_n = A, int(k)
+    cfg.score_thresh, cfg.score_strict = float(score_thresh), 1 if score_strict else 0
+    cfg.min_size = float(min_size)
+    cfg.img_h, cfg.img_w = int(img_size[0]), int(img_size[1])
+    cfg.topk_on_sigmoid = 1 if topk_on_sigmoid else 0
+    for i in range(4):
+        cfg.decode_weights[i] = float(decode_weights[i])
+    cfg.xform_clip = float(xform_clip)
+    boxes = torch.empty((B, L, k, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((B, L, k), dtype=torch.float32, device=dev)
+    index = torch.empty((B, L, k), dtype=torch.int64, device=dev)
+    counts = torch.empty((B, L), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        nbytes = lib.lcr_rpn_select_workspace_bytes(B, L, k)
+        ws = _workspace(nbytes, dev)
+        check(lib.lcr_rpn_select_f32(levels, L, B, C.byref(cfg), boxes.data_ptr(), scores.data_ptr(), index.data_ptr(),
+                                     counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "rpn_select")
+    return boxes, scores, index, counts
+
+
+def nms_batched(boxes: torch.Tensor, scores: Optional[torch.Tensor], iou_threshold: float, *, post_n: int,
+                counts: Optional[torch.Tensor] = None, score_thresh: Optional[float] = None,
+                category: Optional[torch.Tensor] = None):
+    """a8 — greedy NMS over S segments: boxes [S, stride, 4]; scores [S, stride] or None (already
+    sorted); counts [S] i32 or None.  Returns keep [S, post_n] i64 (original in-segment indices, score
+    order) and keep_counts [S] i32."""
+    _need_cuda(boxes, scores, counts, category)
+    b = _f32c(boxes)
+    S, stride = b.shape[0], b.shape[1]
+    s = None if scores is None else _f32c(scores)
+    cn = None if counts is None else counts.to(torch.int32).contiguous()
+    cat = None if category is None else category.to(torch.int32).contiguous()
+    keep = torch.empty((S, post_n), dtype=torch.int64, device=b.device)
+    kc = torch.zeros((S,), dtype=torch.int32, device=b.device)
+    if S == 0 or stride == 0:
+        return keep, kc
+    lib = _lib.load()
+    with torch.cuda.device(b.device):
+        nbytes = lib.lcr_nms_workspace_bytes(S, stride)
+        ws = _workspace(nbytes, b.device)
+        check(lib.lcr_nms_f32(b.data_ptr(), _ptr(s), _ptr(cat), _ptr(cn), S, stride, float(iou_threshold),
+                              0.0 if score_thresh is None else float(score_thresh), 0 if score_thresh is None else 1,
+                              int(post_n), keep.data_ptr(), kc.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "nms")
+    return keep, kc
+
+
+def gather_kept(boxes: torch.Tensor, scores: Optional[torch.Tensor], keep: torch.Tensor, keep_counts: torch.Tensor,
+                want_rois: bool = True, want_valid: bool = False):
+    """proposals[keep] — returns (boxes [S,post_n,4], scores [S,post_n] | None, rois [S*post_n,5] | None
+    [, valid [S*post_n] u8]); padding rows are zero boxes with roi batch index -1 / valid 0."""
+    _need_cuda(boxes, keep, keep_counts)
+    b = _f32c(boxes)
+    S, in_stride = b.shape[0], b.shape[1]
+    post_n = keep.shape[1]
+    s = None if scores is None else _f32c(scores)
+    ob = torch.empty((S, post_n, 4), dtype=torch.float32, device=b.device)
+    osc = None if s is None else torch.empty((S, post_n), dtype=torch.float32, device=b.device)
+    rois = torch.empty((S * post_n, 5), dtype=torch.float32, device=b.device) if want_rois else None
+    valid = torch.empty((S * post_n,), dtype=torch.uint8, device=b.device) if want_valid else None
+    if S:
+        with torch.cuda.device(b.device):
+            check(_lib.load().lcr_gather_kept_f32(b.data_ptr(), _ptr(s), keep.data_ptr(), keep_counts.data_ptr(), S, in_stride,
+                                                  post_n, ob.data_ptr(), _ptr(osc), _ptr(rois), _ptr(valid), _stream()),
+                  "gather_kept")
+    if want_valid:
+        return ob, osc, rois, valid
+    return ob, osc, rois
+
+
+def level_map(boxes: torch.Tensor, k_min: int = 2, k_max: int = 5, canonical_scale: float = 224.0, canonical_level: int = 4,
+              eps: float = 1e-6) -> torch.Tensor:
+    """a11 — LevelMapper (TV:ops/poolers.py:73-84).  boxes [K,4] or rois [K,5] -> levels [K] i32."""
+    _need_cuda(boxes)
+    b = _f32c(boxes)
+    K, bs = b.shape
+    lv = torch.empty((K,), dtype=torch.int32, device=b.device)
+    if K:
+        with torch.cuda.device(b.device):
+            check(_lib.load().lcr_level_map_f32(b.data_ptr(), bs, K, k_min, k_max, float(canonical_scale), canonical_level,
+                                                float(eps), lv.data_ptr(), _stream()), "level_map")
+    return lv
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """[N,C,H,W] tensor -> same logical tensor in channels_last memory, through the tiled transpose
+    kernel when a copy is needed (no-op for tensors that already are NHWC-dense)."""
+    _need_cuda(x)
+    N, Cc, H, W = x.shape
+    if x.dtype == torch.float32 and x.stride() == (H * W * Cc, 1, W * Cc, Cc):
+        return x
+    xc = _f32c(x)
+    out = torch.empty_strided((N, Cc, H, W), (H * W * Cc, 1, W * Cc, Cc), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().lcr_nchw_to_nhwc_f32(xc.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream()), "nchw_to_nhwc")
+    return out
+
+
+def to_nchw(x: torch.Tensor) -> torch.Tensor:
+    """Inverse of to_nhwc: channels_last memory -> contiguous [N,C,H,W]."""
+    _need_cuda(x)
+    N, Cc, H, W = x.shape
+    if x.is_contiguous():
+        return x
+    if x.stride() != (H * W * Cc, 1, W * Cc, Cc):
+        return x.contiguous()
+    out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().lcr_nhwc_to_nchw_f32(x.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream()), "nhwc_to_nchw")
+    return out
+
+
+def _feat_levels(feats: Sequence[torch.Tensor], scales: Sequence[float]):
+    L = len(feats)
+    arr = (LcrFeatLevel * L)()
+    for l, (f, sc) in enumerate(zip(feats, scales)):
+        N, Cc, H, W = f.shape
+        sn, s_c, sh, sw = f.stride()
+        lv = arr[l]
+        lv.data, lv.N, lv.H, lv.W = f.data_ptr(), N, H, W
+        lv.sn, lv.sc, lv.sh, lv.sw = sn, s_c, sh, sw
+        lv.spatial_scale = float(sc)
+    return arr
+
+
+def _dense(f: torch.Tensor) -> bool:
+    N, Cc, H, W = f.shape
+    return f.is_contiguous() or f.stride() == (H * W * Cc, 1, W * Cc, Cc)
+
+
+def roi_align_fwd(feats: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
+                  roi_level: Optional[torch.Tensor], output_size, sampling_ratio: int, aligned: bool) -> torch.Tensor:
+    """a9/a11 — RoIAlign forward over one or several levels.  feats: logical [N,C,H,W] fp32 tensors
+    (NCHW-contiguous or channels_last; other stridings are copied).  rois [K,5]."""
+    feats = [f if (f.dtype == torch.float32 and _dense(f)) else _f32c(f) for f in feats]
+    r = _f32c(rois).reshape(-1, 5)
+    _need_cuda(r, roi_level, *feats)
+    PH, PW = (output_size, output_size) if isinstance(output_size, int) else output_size
+    K, Cc = r.shape[0], feats[0].shape[1]
+    out = torch.empty((K, Cc, PH, PW), dtype=torch.float32, device=r.device)
+    if K == 0:
+        return out
+    lvl = None if roi_level is None else roi_level.to(torch.int32).contiguous()
+    with torch.cuda.device(r.device):
+        check(_lib.load().lcr_roi_align_fwd_f32(_feat_levels(feats, scales), len(feats), Cc, r.data_ptr(), _ptr(lvl), K, PH, PW,
+                                                int(sampling_ratio), 1 if aligned else 0, out.data_ptr(), _stream()),
+              "roi_align_fwd")
+    return out
+
+
+def roi_align_bwd(grad_out: torch.Tensor, grads: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
+                  roi_level: Optional[torch.Tensor], sampling_ratio: int, aligned: bool, zero_grad: bool = True) -> None:
+    """a10 — RoIAlign backward: accumulates into `grads` (dense NCHW or channels_last tensors of the
+    forward feature shapes), zero-filling them first when zero_grad."""
+    g = _f32c(grad_out)
+    r = _f32c(rois).reshape(-1, 5)
+    _need_cuda(g, r, roi_level, *grads)
+    for t in grads:
+        if t.dtype != torch.float32 or not _dense(t):
+            raise _lib.LcrError("roi_align_bwd: grad buffers must be dense fp32 (NCHW or channels_last)")
+    K, Cc, PH, PW = g.shape
+    lvl = None if roi_level is None else roi_level.to(torch.int32).contiguous()
+    with torch.cuda.device(g.device):
+        check(_lib.load().lcr_roi_align_bwd_f32(g.data_ptr(), _feat_levels(grads, scales), len(grads), Cc, r.data_ptr(), _ptr(lvl),
+                                                K, PH, PW, int(sampling_ratio), 1 if aligned else 0, 1 if zero_grad else 0,
+                                                _stream()), "roi_align_bwd")
+
+
+def paste_masks(probs: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int, threshold: float = 0.5,
+                on_value: int = 255, valid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a13 — batched paste/threshold (src/custom_maskrcnn.py:276-295, src/utils/mask_utils.py:149-171).
+    probs [N,M,M] f32, boxes [N,4] f32 -> uint8 [N,H,W] in {0,on_value}."""
+    _need_cuda(probs, boxes, valid, out)
+    p, b = _f32c(probs), _f32c(boxes).reshape(-1, 4)
+    N = b.shape[0]
+    M = p.shape[-1] if p.numel() else 28
+    if out is None:
+        out = torch.empty((N, img_h, img_w), dtype=torch.uint8, device=b.device)
+    elif out.dtype != torch.uint8 or not out.is_contiguous() or out.numel() < N * img_h * img_w:
+        raise _lib.LcrError("paste_masks: out must be a contiguous uint8 buffer of at least N*H*W bytes")
+    v = None if valid is None else valid.to(torch.uint8).contiguous()
+    if N:
+        with torch.cuda.device(b.device):
+            check(_lib.load().lcr_paste_masks_u8(p.data_ptr(), b.data_ptr(), _ptr(v), N, M, img_h, img_w, float(threshold),
+                                                 int(on_value), out.data_ptr(), _stream()), "paste_masks")
+    return out
+
+
+def pack_records(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """Detection records [S, stride, 6] = (x1,y1,x2,y2,score,label=1), zero padded."""
+    _need_cuda(boxes, scores, counts)
+    b, s = _f32c(boxes), _f32c(scores)
+    S, stride = s.shape
+    cn = counts.to(torch.int32).contiguous()
+    rec = torch.empty((S, stride, 6), dtype=torch.float32, device=b.device)
+    if S:
+        with torch.cuda.device(b.device):
+            check(_lib.load().lcr_pack_records_f32(b.data_ptr(), s.data_ptr(), cn.data_ptr(), S, stride, rec.data_ptr(), _stream()),
+                  "pack_records")
+    return rec

@@ -1,0 +1,152 @@
+"""Drop-ins for the three torchvision operators the reference imports
+(``from torchvision.ops import RoIAlign, nms, box_iou`` — src/custom_maskrcnn.py:5):
+
+* ``RoIAlign`` — parameter-free nn.Module (checkpoints interchange; count_parameters keeps reporting
+  ``roi_align: 0``), differentiable w.r.t. the feature map through ``_RoIAlignFn``.
+* ``nms`` / ``batched_nms`` — same signatures and return type (int64 kept indices, score order).
+* ``MultiScaleRoIAlign`` — the multi-level pooler of the transfer model (TV:ops/poolers.py:230-321),
+  level assignment + all levels in ONE launch.
+``box_iou`` is loss-side (SURVEY §8f "next") and stays torchvision's.
+"""
+from __future__ import annotations
+
+from typing import Sequence, Union
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+def convert_boxes_to_roi_format(boxes: Sequence[torch.Tensor]) -> torch.Tensor:
+    """list[Tensor[K_i,4]] -> Tensor[K,5] with the image index in column 0 (TV:ops/_utils.py:18-25)."""
+    ids = [torch.full((b.shape[0], 1), float(i), dtype=b.dtype, device=b.device) for i, b in enumerate(boxes)]
+    return torch.cat([torch.cat(ids, dim=0), torch.cat(list(boxes), dim=0)], dim=1)
+
+
+def _as_rois(rois) -> torch.Tensor:
+    if isinstance(rois, (list, tuple)):
+        return convert_boxes_to_roi_format(rois)
+    return rois
+
+
+def _prefer_nhwc(x: torch.Tensor, K: int, PH: int, PW: int) -> bool:
+    """NCHW-contiguous input: transposing the map pays off once the pooled output outweighs it."""
+    N, C, H, W = x.shape
+    return K * PH * PW >= N * H * W
+
+
+class _RoIAlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats_and_meta, *feats):
+        scales, rois, roi_level, output_size, sampling_ratio, aligned = feats_and_meta
+        PH, PW = output_size
+        K = rois.shape[0]
+        used = []
+        for f in feats:
+            N, C, H, W = f.shape
+            nhwc_dense = f.dtype == torch.float32 and f.stride() == (H * W * C, 1, W * C, C)
+            if not nhwc_dense and sampling_ratio == 2 and PH == PW and PH in (7, 14) and C % 4 == 0 and _prefer_nhwc(f, K, PH, PW):
+                f = ops.to_nhwc(f)
+            used.append(f)
+        out = ops.roi_align_fwd(used, scales, rois, roi_level, (PH, PW), sampling_ratio, aligned)
+        ctx.meta = (scales, output_size, sampling_ratio, aligned, [tuple(f.shape) for f in feats])
+        ctx.save_for_backward(rois, roi_level if roi_level is not None else torch.empty(0, device=rois.device))
+        ctx.has_level = roi_level is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        scales, output_size, sampling_ratio, aligned, shapes = ctx.meta
+        rois, roi_level = ctx.saved_tensors
+        roi_level = roi_level if ctx.has_level else None
+        grads = []
+        for (N, C, H, W) in shapes:
+            # channels_last grad buffers: the backward fast path scatters whole channel vectors
+            grads.append(torch.empty_strided((N, C, H, W), (H * W * C, 1, W * C, C), dtype=torch.float32, device=grad_out.device))
+        ops.roi_align_bwd(grad_out, grads, scales, rois, roi_level, sampling_ratio, aligned, zero_grad=True)
+        return (None, *grads)
+
+
+def roi_align(input: torch.Tensor, boxes, output_size, spatial_scale: float = 1.0, sampling_ratio: int = -1,
+              aligned: bool = False) -> torch.Tensor:
+    """torchvision.ops.roi_align signature (TV:ops/roi_align.py:204-260)."""
+    rois = _as_rois(boxes)
+    if isinstance(output_size, int):
+        output_size = (output_size, output_size)
+    sr = max(int(sampling_ratio), 0)  # torchvision: <= 0 means adaptive
+    return _RoIAlignFn.apply(((float(spatial_scale),), rois, None, tuple(output_size), sr, bool(aligned)), input)
+
+
+class RoIAlign(nn.Module):
+    """torchvision.ops.RoIAlign drop-in (TV:ops/roi_align.py:263-283) as constructed at
+    src/custom_maskrcnn.py:48-50: RoIAlign(output_size=(7,7), spatial_scale=0.25, sampling_ratio=2).
+    No parameters, no buffers."""
+
+    def __init__(self, output_size, spatial_scale: float, sampling_ratio: int, aligned: bool = False):
+        super().__init__()
+        self.output_size = output_size
+        self.spatial_scale = spatial_scale
+        self.sampling_ratio = sampling_ratio
+        self.aligned = aligned
+
+    def forward(self, input: torch.Tensor, rois: Union[torch.Tensor, Sequence[torch.Tensor]]) -> torch.Tensor:
+        return roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned)
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(output_size={self.output_size}, spatial_scale={self.spatial_scale}, "
+                f"sampling_ratio={self.sampling_ratio}, aligned={self.aligned})")
+
+
+class MultiScaleRoIAlign(nn.Module):
+    """Multi-level pooler with torchvision semantics (TV:ops/poolers.py:230-321): scales inferred as
+    2^-k from the feature/image sizes, LevelMapper(k_min, k_max, 224, 4), one launch for all levels."""
+
+    def __init__(self, featmap_names, output_size, sampling_ratio, *, canonical_scale: int = 224, canonical_level: int = 4):
+        super().__init__()
+        self.featmap_names = list(featmap_names)
+        self.output_size = (output_size, output_size) if isinstance(output_size, int) else tuple(output_size)
+        self.sampling_ratio = sampling_ratio
+        self.canonical_scale = canonical_scale
+        self.canonical_level = canonical_level
+
+    @staticmethod
+    def infer_scales(feats, image_shapes):
+        import math
+        max_h = max(s[0] for s in image_shapes)
+        scales = []
+        for f in feats:
+            approx = float(f.shape[-2]) / float(max_h)
+            scales.append(2.0 ** float(round(math.log2(approx))))
+        return scales
+
+    def forward(self, x, boxes, image_shapes):
+        feats = [x[k] for k in self.featmap_names] if isinstance(x, dict) else list(x)
+        rois = _as_rois(boxes)
+        scales = self.infer_scales(feats, image_shapes)
+        import math
+        k_min, k_max = int(-math.log2(scales[0])), int(-math.log2(scales[-1]))
+        levels = ops.level_map(rois, k_min, k_max, float(self.canonical_scale), self.canonical_level) if len(feats) > 1 else None
+        sr = max(int(self.sampling_ratio), 0)
+        return _RoIAlignFn.apply((tuple(scales), rois, levels, self.output_size, sr, False), *feats)
+
+
+def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    """torchvision.ops.nms drop-in (TV:ops/boxes.py:20-48): int64 indices of the kept boxes, sorted by
+    decreasing score.  One host sync (the dense return type needs the count)."""
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    keep, kc = ops.nms_batched(boxes.reshape(1, n, 4), scores.reshape(1, n), float(iou_threshold), post_n=n)
+    return keep[0, : int(kc.item())].clone()
+
+
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    """torchvision.ops.batched_nms drop-in (TV:ops/boxes.py:51-120), per-category semantics (boxes of
+    different categories never interact), evaluated exactly — no coordinate-offset rounding."""
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    keep, kc = ops.nms_batched(boxes.reshape(1, n, 4), scores.reshape(1, n), float(iou_threshold), post_n=n,
+                               category=idxs.reshape(1, n))
+    return keep[0, : int(kc.item())].clone()

@@ -1,0 +1,129 @@
+"""GPU parity: RoIAlign forward / backward: within 1e-5 relative (fp32),
+against the golden outputs of the compiled torchvision CPU op, the oracle, and torchvision's CUDA op."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # north star: "RoIAlign forward/backward ... within 1e-5 relative error in fp32"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from livecell_instance_segmentation_b200 import ops as o
+    return o
+
+
+CASES = [("p7", 7, 2, False), ("p14", 14, 2, False), ("p7a", 7, 2, True), ("p7ad", 7, 0, False)]
+
+
+@pytest.mark.parametrize("tag,P,sr,al", CASES)
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_forward_golden(ops, golden, tag, P, sr, al, layout):
+    from gpu_util import N, T, nhwc, assert_close_rel
+    g = golden("roi_align")
+    feat = T(g["feat"])
+    if layout == "nhwc":
+        feat = nhwc(feat)                      # TMA fast path for sr == 2, generic kernel otherwise
+    out = ops.roi_align_fwd([feat], [0.25], T(g["rois"]), None, (P, P), sr, al)
+    assert_close_rel(N(out), g[f"out_{tag}"], RTOL)
+
+
+@pytest.mark.parametrize("tag,P,sr,al", CASES)
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_backward_golden(ops, golden, tag, P, sr, al, layout):
+    from gpu_util import N, T, assert_close_rel
+    g = golden("roi_align")
+    shape = g["feat"].shape
+    gin = torch.full(shape, 7.0, device="cuda:0")           # must be zero-filled by the callee
+    if layout == "nhwc":
+        gin = gin.contiguous(memory_format=torch.channels_last)
+    ops.roi_align_bwd(T(g[f"gout_{tag}"]), [gin], [0.25], T(g["rois"]), None, sr, al, zero_grad=True)
+    assert_close_rel(N(gin), g[f"gin_{tag}"], RTOL)
+
+
+def test_module_and_autograd(golden):
+    from gpu_util import N, T, assert_close_rel
+    from livecell_instance_segmentation_b200.roi_align import RoIAlign
+    g = golden("roi_align")
+    op = RoIAlign(output_size=(7, 7), spatial_scale=1.0 / 4.0, sampling_ratio=2)      # custom_maskrcnn.py:48-50
+    assert sum(p.numel() for p in op.parameters()) == 0 and len(list(op.buffers())) == 0
+    # reference call form: feature_map[b:b+1], [proposals]
+    out = op(T(g["feat"][:1]), [T(g["rois"][:, 1:])])
+    assert_close_rel(N(out), g["out_listform"], RTOL)
+    f = T(g["feat"]).requires_grad_(True)
+    y = op(f, T(g["rois"]))
+    y.backward(T(g["gout_p7"]))
+    assert_close_rel(N(y), g["out_p7"], RTOL)
+    assert_close_rel(N(f.grad), g["gin_p7"], RTOL)
+    assert op(T(g["feat"][:1]), [T(np.zeros((0, 4), np.float32))]).shape == (0, 8, 7, 7)
+
+
+@pytest.mark.parametrize("P", [7, 14])
+def test_c1_shape_vs_oracle_and_torchvision(ops, oracle, synth, P):
+    """Level-0 map of a 704x520 frame, 256 channels, anchor-shaped + edge-case RoIs."""
+    import torchvision
+    from gpu_util import N, T, nhwc, assert_close_rel
+    C, H, W, K = 256, 130, 176, 96
+    feat = synth.make_features(1, C, H, W, seed=5)
+    rois = synth.make_rois(K, 6, edge_cases=True)
+    ref = oracle.roi_align_fwd(feat, rois, P, P, 0.25, 2, False)
+    ft = T(feat)
+    fast = ops.roi_align_fwd([nhwc(ft)], [0.25], T(rois), None, (P, P), 2, False)
+    gen = ops.roi_align_fwd([ft], [0.25], T(rois), None, (P, P), 2, False)
+    assert_close_rel(N(fast), ref, RTOL)
+    assert_close_rel(N(gen), ref, RTOL)
+    tv = torchvision.ops.roi_align(ft, T(rois), (P, P), 0.25, 2, False)
+    assert_close_rel(N(fast), N(tv), RTOL)
+    # backward: all-ones grad, sum(grad_in) == sum(grad_out) for in-range RoIs
+    inr = synth.make_rois(64, 7)
+    gout = torch.ones((64, C, P, P), device="cuda:0")
+    gin = torch.empty((1, C, H, W), device="cuda:0").contiguous(memory_format=torch.channels_last)
+    ops.roi_align_bwd(gout, [gin], [0.25], T(inr), None, 2, False)
+    assert abs(float(gin.double().sum()) - 64 * C * P * P) < 1e-3 * 64 * C * P * P
+    rng = np.random.RandomState(8)
+    go = rng.standard_normal((K, C, P, P)).astype(np.float32)
+    ref_b = oracle.roi_align_bwd(go, rois, (1, C, H, W), 0.25, 2, False)
+    gin2 = torch.empty((1, C, H, W), device="cuda:0").contiguous(memory_format=torch.channels_last)
+    ops.roi_align_bwd(T(go), [gin2], [0.25], T(rois), None, 2, False)
+    assert_close_rel(N(gin2), ref_b, RTOL)
+    gin3 = torch.empty((1, C, H, W), device="cuda:0")
+    ops.roi_align_bwd(T(go), [gin3], [0.25], T(rois), None, 2, False)     # generic (NCHW) path
+    assert_close_rel(N(gin3), ref_b, RTOL)
+
+
+def test_padding_rois_and_batch(ops, oracle, synth):
+    from gpu_util import N, T, nhwc, assert_close_rel
+    feat = synth.make_features(3, 64, 20, 24, seed=12)
+    rois = synth.make_rois(40, 13, img_h=80, img_w=96, batch=3)
+    rois[5, 0] = -1.0
+    rois[17, 0] = -1.0
+    ref = oracle.roi_align_fwd(feat, rois)
+    out = ops.roi_align_fwd([nhwc(T(feat))], [0.25], T(rois), None, (7, 7), 2, False)
+    assert_close_rel(N(out), ref, RTOL)
+    assert float(out[5].abs().max()) == 0.0 and float(out[17].abs().max()) == 0.0
+    out2 = ops.roi_align_fwd([T(feat)], [0.25], T(rois), None, (7, 7), 2, False)
+    assert_close_rel(N(out2), ref, RTOL)
+
+
+def test_multiscale_golden(golden, synth):
+    from gpu_util import N, T, nhwc, assert_close_rel
+    from livecell_instance_segmentation_b200.roi_align import MultiScaleRoIAlign
+    g = golden("roi_align")
+    feats = [T(synth.make_features(1, 8, 32 >> i, 40 >> i, seed=40 + i)) for i in range(4)]
+    ms = MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+    out = ms({str(i): f for i, f in enumerate(feats)}, [T(g["ms_boxes"])], [(128, 160)])
+    assert_close_rel(N(out), g["ms_out"], RTOL)
+    out2 = ms({str(i): nhwc(f) for i, f in enumerate(feats)}, [T(g["ms_boxes"])], [(128, 160)])
+    assert_close_rel(N(out2), g["ms_out"], RTOL)
+
+
+def test_layout_helpers(ops, synth):
+    from gpu_util import N, T
+    x = synth.make_features(2, 37, 19, 23, seed=3)
+    y = ops.to_nhwc(T(x))
+    assert y.stride() == (19 * 23 * 37, 1, 23 * 37, 37)
+    assert np.array_equal(N(y), x)
+    z = ops.to_nchw(y)
+    assert z.is_contiguous() and np.array_equal(N(z), x)

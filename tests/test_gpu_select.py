@@ -1,0 +1,170 @@
+"""GPU parity: RPN proposal selection against the oracle and the
+reference-generated golden vectors.  Indices and boxes bit-exact (tie-free fixtures), scores 1e-6."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from livecell_instance_segmentation_b200 import ops as o
+    return o
+
+
+def run_select(ops, obj, **kw):
+    from gpu_util import N, T
+    boxes, scores, index, counts = ops.rpn_select([T(obj)], **kw)
+    torch.cuda.synchronize()
+    return N(boxes), N(scores), N(index), N(counts)
+
+
+def check_against_oracle(ops, oracle, obj, k, thr, min_size, H, W, base, stride=4, strict=True, on_sigmoid=True):
+    gb, gs, gi, gc = run_select(ops, obj, k=k, img_size=(H, W), score_thresh=thr, min_size=min_size, strides=[stride],
+                                base=torch.from_numpy(base), score_strict=strict, topk_on_sigmoid=on_sigmoid)
+    for b in range(obj.shape[0]):
+        ob, os_, oi = oracle.rpn_select(obj[b], base=base, stride=stride, k=k, score_thresh=thr, score_strict=strict,
+                                        min_size=min_size, img_h=H, img_w=W, topk_on_sigmoid=on_sigmoid)
+        n = int(gc[b, 0])
+        assert n == len(oi), (b, n, len(oi))
+        assert np.array_equal(gi[b, 0, :n], oi)
+        assert np.array_equal(gb[b, 0, :n], ob)
+        np.testing.assert_allclose(gs[b, 0, :n], os_, rtol=0, atol=1e-6)
+
+
+def test_small_golden(ops, golden, oracle):
+    g = golden("proposals")
+    base = oracle.base_anchors()
+    obj = g["small_obj"]
+    gb, gs, gi, gc = run_select(ops, obj, k=100, img_size=(96, 128), score_thresh=-1.0, min_size=0.0, strides=[4],
+                                base=torch.from_numpy(base))
+    for b in range(2):
+        assert int(gc[b, 0]) == 100
+        assert np.array_equal(gi[b, 0], g[f"small_topk_index_{b}"])          # torch.topk indices (tie-free)
+        np.testing.assert_allclose(gs[b, 0], g[f"small_topk_scores_{b}"], rtol=0, atol=1e-6)
+    # training proposals: reference output of generate_training_proposals
+    gb, gs, gi, gc = run_select(ops, obj, k=120, img_size=(96, 128), score_thresh=0.01, min_size=5, strides=[4],
+                                base=torch.from_numpy(base))
+    for b in range(2):
+        assert np.array_equal(gb[b, 0, : gc[b, 0]], g[f"small_train_boxes_{b}"])
+    check_against_oracle(ops, oracle, obj, 100, 0.3, 10, 96, 128, base)
+
+
+@pytest.mark.parametrize("tag,seed,n_cells,k", [("c1", 21, 150, 250), ("c3", 23, 2000, 2000)])
+def test_full_size_golden(ops, golden, oracle, synth, tag, seed, n_cells, k):
+    g = golden("proposals")
+    base = oracle.base_anchors()
+    obj = synth.make_objectness(1, 9, 130, 176, n_cells=n_cells, seed=seed, k=k)
+    gb, gs, gi, gc = run_select(ops, obj, k=k, img_size=(520, 704), score_thresh=-1.0, min_size=0.0, strides=[4],
+                                base=torch.from_numpy(base))
+    assert int(gc[0, 0]) == k
+    assert np.array_equal(gi[0, 0], g[f"{tag}_topk_index"])
+    check_against_oracle(ops, oracle, obj, k, 0.3, 10, 520, 704, base)
+
+
+def test_c2_training_golden(ops, golden, oracle, synth):
+    g = golden("proposals")
+    base = oracle.base_anchors()
+    obj = synth.make_objectness(1, 9, 64, 64, n_cells=20, seed=int(g["c2_seed"]), k=500)
+    gb, gs, gi, gc = run_select(ops, obj, k=500, img_size=(256, 256), score_thresh=0.01, min_size=5, strides=[4],
+                                base=torch.from_numpy(base))
+    assert np.array_equal(gb[0, 0, : gc[0, 0]], g["c2_train_boxes"])
+
+
+def test_batched_and_odd_shapes(ops, oracle, synth):
+    base = oracle.base_anchors()
+    # batch of 5 images of the real 300x222 tile geometry (56x75 map: P not divisible by 8 or 4)
+    obj = synth.make_objectness(5, 9, 56, 75, n_cells=60, seed=71, k=300)
+    check_against_oracle(ops, oracle, obj, 300, 0.3, 10, 222, 300, base)
+    # tiny map: k > n
+    obj = synth.make_objectness(2, 9, 3, 5, n_cells=4, seed=72, k=134)
+    check_against_oracle(ops, oracle, obj, 500, -1.0, 0.0, 12, 20, base)
+    # 3 anchors, stride 16, k = 1
+    b3 = np.array([[-8, -4, 8, 4], [-4, -8, 4, 8], [-6.5, -6.5, 6.5, 6.5]], np.float32)
+    obj = synth.make_objectness(2, 3, 17, 22, n_cells=10, seed=73, k=1)
+    check_against_oracle(ops, oracle, obj, 1, 0.0, 1.0, 272, 352, b3, stride=16)
+
+
+def test_anchor_tensor_gather_matches_generated(ops, oracle, synth):
+    from gpu_util import N, T, DEV
+    base = oracle.base_anchors()
+    obj = synth.make_objectness(2, 9, 24, 32, n_cells=40, seed=74, k=100)
+    anc = ops.anchors(24, 32, 4, torch.from_numpy(base), DEV)
+    a = [N(t) for t in ops.rpn_select([T(obj)], k=100, img_size=(96, 128), score_thresh=0.3, min_size=10, anchors_per_level=[anc])]
+    b = [N(t) for t in ops.rpn_select([T(obj)], k=100, img_size=(96, 128), score_thresh=0.3, min_size=10, strides=[4],
+                                      base=torch.from_numpy(base))]
+    assert np.array_equal(a[3], b[3])
+    for i in range(2):
+        n = int(a[3][i, 0])
+        for x, y in zip(a[:3], b[:3]):
+            assert np.array_equal(x[i, 0, :n], y[i, 0, :n])
+
+
+def test_ties_follow_index_order(ops, oracle):
+    """torch.topk leaves tie order unspecified; ours is (score desc, flat index asc) — the oracle's rule."""
+    base = oracle.base_anchors()
+    rng = np.random.RandomState(3)
+    # (a) all logits equal: the k lowest flat indices win
+    obj = np.full((1, 9, 20, 24), 0.75, np.float32)
+    check_against_oracle(ops, oracle, obj, 100, -1.0, 0.0, 80, 96, base)
+    # (b) saturated sigmoid: 300 logits > 17 all map to 1.0f, k = 250 straddles the tie group
+    obj = rng.normal(-4, 1, size=(2, 9, 20, 24)).astype(np.float32)
+    flat = obj.reshape(2, -1)
+    for b in range(2):
+        flat[b, rng.choice(flat.shape[1], 300, replace=False)] = rng.uniform(17.5, 30, size=300).astype(np.float32)
+    check_against_oracle(ops, oracle, obj, 250, 0.3, 0.0, 80, 96, base)
+    # (c) heavy duplicates: logits quantised to 16 values
+    obj = np.round(rng.normal(0, 1, size=(1, 9, 20, 24)) * 4).astype(np.float32) / 4
+    obj = np.clip(obj, -2, 1.75)
+    check_against_oracle(ops, oracle, obj, 333, -1.0, 0.0, 80, 96, base)
+    # (d) NaN ranks highest and is then dropped by `score > thr`
+    obj = rng.normal(-4, 1, size=(1, 9, 20, 24)).astype(np.float32)
+    obj[0, 2, 3, 4] = np.nan
+    obj[0, 0, 0, 0] = 5.0
+    check_against_oracle(ops, oracle, obj, 50, 0.0, 0.0, 80, 96, base)
+
+
+def test_torchvision_mode_with_decode(ops, oracle, synth):
+    """P2 semantics (TV:models/detection/rpn.py:231-297): top-k on logits, decode, `>=` threshold,
+    min_size 1e-3, two levels in one launch."""
+    from gpu_util import N, T
+    rng = np.random.RandomState(5)
+    bases = [np.array([[-16, -8, 16, 8], [-11, -11, 11, 11], [-8, -16, 8, 16]], np.float32),
+             np.array([[-32, -16, 32, 16], [-23, -23, 23, 23], [-16, -32, 16, 32]], np.float32)]
+    shapes, strides = [(32, 40), (16, 20)], [4, 8]
+    objs = [synth.make_objectness(2, 3, h, w, n_cells=30, seed=80 + i, k=200) for i, (h, w) in enumerate(shapes)]
+    dls = [rng.normal(0, 0.2, size=(2, 12, h, w)).astype(np.float32) for (h, w) in shapes]
+    gb, gs, gi, gc = ops.rpn_select([T(o) for o in objs], k=200, img_size=(128, 160), score_thresh=0.05, min_size=1e-3,
+                                    strides=strides, base=[torch.from_numpy(b) for b in bases], deltas=[T(d) for d in dls],
+                                    score_strict=False, topk_on_sigmoid=False)
+    gb, gs, gi, gc = N(gb), N(gs), N(gi), N(gc)
+    for b in range(2):
+        for l in range(2):
+            ob, os_, oi = oracle.rpn_select(objs[l][b], base=bases[l], stride=strides[l], k=200, score_thresh=0.05,
+                                            score_strict=False, min_size=1e-3, img_h=128, img_w=160, topk_on_sigmoid=False,
+                                            deltas=dls[l][b])
+            n = int(gc[b, l])
+            assert n == len(oi)
+            assert np.array_equal(gi[b, l, :n], oi)
+            np.testing.assert_allclose(gb[b, l, :n], ob, rtol=1e-5, atol=1e-4)
+            np.testing.assert_allclose(gs[b, l, :n], os_, rtol=0, atol=1e-6)
+
+
+def test_uncached_large_map(ops, oracle, synth):
+    """Maps whose per-CTA slice exceeds the shared-memory key cache re-read L2 instead (same result)."""
+    base = oracle.base_anchors()
+    obj = synth.make_objectness(1, 9, 260, 352, n_cells=300, seed=91, k=1000)   # 823 680 logits
+    check_against_oracle(ops, oracle, obj, 1000, 0.3, 10, 1040, 1408, base)
+
+
+def test_error_paths(ops):
+    from gpu_util import T
+    from livecell_instance_segmentation_b200._lib import LcrError
+    obj = T(np.zeros((1, 9, 4, 4), np.float32))
+    with pytest.raises(LcrError):
+        ops.rpn_select([obj], k=9000, img_size=(16, 16), score_thresh=0.0, min_size=0.0, strides=[4],
+                       base=ops.base_anchors())                      # k > LCR_MAX_TOPK
+    with pytest.raises(LcrError):
+        ops.rpn_select([obj.cpu()], k=10, img_size=(16, 16), score_thresh=0.0, min_size=0.0, strides=[4],
+                       base=ops.base_anchors())                      # CPU tensor: no fallback

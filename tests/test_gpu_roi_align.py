@@ -74,8 +74,11 @@ def test_c1_shape_vs_oracle_and_torchvision(ops, oracle, synth, P):
     gen = ops.roi_align_fwd([ft], [0.25], T(rois), None, (P, P), 2, False)
     assert_close_rel(N(fast), ref, RTOL)
     assert_close_rel(N(gen), ref, RTOL)
+    # torchvision's CUDA op itself deviates from its CPU op (the parity target) by up to ~2e-5 relative:
+    # nvcc contracts its sample-coordinate expression, and one ulp of a coordinate near 130 (1.5e-5) moves
+    # a bilinear weight by as much.  Cross-check only, at 1e-4.
     tv = torchvision.ops.roi_align(ft, T(rois), (P, P), 0.25, 2, False)
-    assert_close_rel(N(fast), N(tv), RTOL)
+    assert_close_rel(N(fast), N(tv), 1e-4)
     # backward: all-ones grad, sum(grad_in) == sum(grad_out) for in-range RoIs
     inr = synth.make_rois(64, 7)
     gout = torch.ones((64, C, P, P), device="cuda:0")

@@ -1,0 +1,22 @@
+#!/bin/bash
+# Runs on the GPU box (under gpurun): per-file GPU parity tests (separate processes so that a faulting
+# kernel cannot poison the other files), smoke(), then a short bench.  Logs land in gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+status=0
+for f in tests/test_gpu_boxes.py tests/test_gpu_select.py tests/test_gpu_nms.py tests/test_gpu_roi_align.py tests/test_gpu_paste.py tests/test_gpu_pipeline.py; do
+  name=$(basename $f .py)
+  timeout 600 python -m pytest $f -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/$name.log 2>&1
+  rc=$?
+  echo "$name rc=$rc: $(tail -1 gpurun_out/$name.log)"
+  [ $rc -ne 0 ] && status=1
+done
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke rc=$?: $(tail -1 gpurun_out/smoke.log)"
+if [ "$1" != "--no-bench" ]; then
+  timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+  echo "bench rc=$?"
+  tail -c 3000 gpurun_out/bench.json
+  tail -5 gpurun_out/bench.err
+fi
+exit $status

@@ -5,8 +5,9 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain_bench.json 2> gpurun_out/plain_bench.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-CMD2="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --frames 16"
-$CMD2 > gpurun_out/plain_bench16.json 2> gpurun_out/plain_bench16.err &&
-ncu --set full --clock-control none --import-source on -k regex:"roi_fwd_nhwc|paste_rows16|rpn_select_kernel|nms_resolve|nms_mask" -s 60 -c 5 -o gpurun_out/prof_full $CMD2 > gpurun_out/ncu_full.log 2>&1
+# one whole timed step of the region kernels (7 matching launches per step; skip the 3 warm-up steps)
+ncu --set full --clock-control none --import-source on \
+    -k regex:"roi_fwd_nhwc|paste_rows16|rpn_select_kernel|nms_resolve|nms_mask" -s 21 -c 7 \
+    -f -o gpurun_out/prof_full $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out/

@@ -9,6 +9,9 @@
 // Layout: out [N, H, W] u8; a thread owns one 16-byte column segment of the frame and walks down
 // the rows of its band, so no per-vector integer division is needed; stores are st.global.cs
 // (streaming: the 183 MB/image of masks must not evict the L2-resident feature maps).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace lcr {
@@ -107,6 +110,126 @@ __global__ void __launch_bounds__(512) paste_rows16_kernel(const float* __restri
   }
 }
 
+// ---- TMA path ------------------------------------------------------------------------------------
+// A frame is >99 % zeros: only the rows y1..y2 of the box carry data.  The SM therefore does not
+// execute one store instruction per 16 bytes; it hands the copy engine a few large bulk stores
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP):
+//   * rows above / below the box: straight from a zero-filled shared buffer (ZB bytes per store),
+//   * box rows: composed (bilinear + threshold) into a double-buffered row chunk in shared memory,
+//     one bulk store per chunk of RB / W rows.
+// One CTA per detection (persistent), thread 0 issues and tracks the bulk groups; instruction issue
+// drops from ~100 per 512 bytes to a handful per frame, leaving the kernel on the HBM write roofline.
+__device__ __forceinline__ void paste_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void paste_bulk_store(void* gdst, const void* ssrc, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void paste_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void paste_bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void paste_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// bilinear + threshold with the probabilities staged in shared memory (same expression tree as paste_pixel)
+__device__ __forceinline__ bool paste_pixel_smem(const float* prob, int M, int h0, int h1, float wy0, float wy1, float sw, int dx,
+                                                 float thr) {
+  int w0, w1;
+  float wx0, wx1;
+  src_index(sw, dx, M, w0, w1, wx0, wx1);
+  const float a = prob[h0 * M + w0], b = prob[h0 * M + w1];
+  const float c = prob[h1 * M + w0], d = prob[h1 * M + w1];
+  const float top = __fmaf_rn(a, wx0, __fmul_rn(b, wx1));
+  const float bot = __fmaf_rn(c, wx0, __fmul_rn(d, wx1));
+  const float v = __fmaf_rn(top, wy0, __fmul_rn(bot, wy1));
+  return v > thr;
+}
+
+constexpr int kPasteThreads = 128;
+constexpr int kPasteZB = 16 * 1024;   // zero buffer
+constexpr int kPasteRB = 11 * 1024;   // one row chunk (16 rows of a 704-px frame)
+
+__global__ void __launch_bounds__(kPasteThreads) paste_bulk_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
+                                                                   const uint8_t* __restrict__ valid, int N, int M, int H, int W,
+                                                                   float thr, uint32_t on_value, uint8_t* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint8_t* zb = smem;
+  uint8_t* rb = smem + kPasteZB;                                               // two chunks of kPasteRB bytes
+  float* sprob = reinterpret_cast<float*>(smem + kPasteZB + 2 * kPasteRB);    // [M*M]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kPasteZB / 16; i += kPasteThreads) reinterpret_cast<uint4*>(zb)[i] = make_uint4(0u, 0u, 0u, 0u);
+  paste_fence_async();
+  __syncthreads();
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  const int vpr = W / 16;
+  const int chunk_rows = max(1, min(kPasteRB / W, H));
+  const int MM = M * M;
+  int buf = 0;
+
+  for (int det = blockIdx.x; det < N; det += gridDim.x) {
+    if (valid && !valid[det]) continue;  // block-uniform
+    const PasteBox pb = make_paste_box(boxes, det, M, H, W);
+    uint8_t* frame = out + (size_t)det * H * W;
+    const int y1 = pb.live ? pb.y1 : 0, y2 = pb.live ? pb.y2 : 0;
+    if (tid == 0) {  // rows [0, y1) and [y2, H) are zeros: bulk stores from the zero buffer, joined to the next commit
+      for (int part = 0; part < 2; ++part) {
+        size_t a = part == 0 ? 0 : (size_t)y2 * W;
+        const size_t b = part == 0 ? (size_t)y1 * W : (size_t)H * W;
+        while (a < b) {
+          const uint32_t n = (uint32_t)min((size_t)kPasteZB, b - a);
+          paste_bulk_store(frame + a, zb, n, pol);
+          a += n;
+        }
+      }
+    }
+    if (!pb.live) {
+      if (tid == 0) paste_bulk_commit();
+      continue;
+    }
+    // the previous frame's readers of sprob passed the barrier that followed their last chunk
+    const float* prob = probs + (size_t)det * MM;
+    for (int i = tid; i < MM; i += kPasteThreads) sprob[i] = __ldg(prob + i);
+    for (int yc = y1; yc < y2; yc += chunk_rows) {
+      const int rows = min(chunk_rows, y2 - yc);
+      uint8_t* chunk = rb + buf * kPasteRB;
+      if (tid == 0) paste_bulk_wait_read_1();  // the store issued two chunks ago has finished reading this buffer
+      __syncthreads();                         // (also publishes sprob)
+      for (int r = warp; r < rows; r += kPasteThreads / 32) {
+        int h0, h1;
+        float wy0, wy1;
+        src_index(pb.sh, yc + r - pb.y1, M, h0, h1, wy0, wy1);
+        for (int xv = lane; xv < vpr; xv += 32) {
+          const int x0 = xv * 16;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (x0 < pb.x2 && x0 + 16 > pb.x1) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t word = 0u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int x = x0 + q * 4 + j;
+                if (x >= pb.x1 && x < pb.x2 && paste_pixel_smem(sprob, M, h0, h1, wy0, wy1, pb.sw, x - pb.x1, thr))
+                  word |= on_value << (8 * j);
+              }
+              w[q] = word;
+            }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          *reinterpret_cast<uint4*>(chunk + (size_t)r * W + x0) = v;
+        }
+      }
+      paste_fence_async();
+      __syncthreads();
+      if (tid == 0) {
+        paste_bulk_store(frame + (size_t)yc * W, chunk, (uint32_t)(rows * W), pol);
+        paste_bulk_commit();
+      }
+      buf ^= 1;
+    }
+  }
+  if (tid == 0) paste_bulk_wait_all();
+}
+
 // Generic path (any W / alignment): one thread per pixel, byte stores.  Correctness path for odd
 // frame widths (e.g. the reference's 300x222 tiles are fine: 300 % 4 == 0 but 300 % 16 != 0).
 __global__ void __launch_bounds__(256) paste_generic_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
@@ -146,6 +269,26 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
   LCR_REQUIRE((int64_t)H * W < (1ll << 31), LCR_ERR_CAPACITY);
   const int vpr = W / 16;
   const bool fast = (W % 16 == 0) && aligned_to(out, 16) && vpr <= 512;
+  const char* mode = getenv("LCR_PASTE");  // tuning switch for A/B runs: "rows16" selects the per-thread store kernel
+  const size_t bulk_smem = (size_t)kPasteZB + 2 * kPasteRB + round_up(sizeof(float) * (size_t)M * M, 16);
+  if (fast && W <= kPasteRB && bulk_smem <= 100 * 1024 && !(mode && strcmp(mode, "rows16") == 0)) {
+    static thread_local int configured_dev = -1;
+    static thread_local size_t configured_smem = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev || configured_smem < bulk_smem) {
+      cudaError_t e = cudaFuncSetAttribute(paste_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem);
+      if (e != cudaSuccess) return cuda_status(e);
+      configured_dev = dev;
+      configured_smem = bulk_smem;
+    }
+    const int per_sm = (int)((227 * 1024) / (bulk_smem + 1024));
+    const long long max_blocks = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
+    const int blocks = (int)((long long)N < max_blocks ? N : max_blocks);
+    paste_bulk_kernel<<<blocks, kPasteThreads, bulk_smem, as_stream(stream)>>>(probs, boxes, valid, N, M, H, W, threshold,
+                                                                              (uint32_t)on_value, out);
+    return after_launch();
+  }
   if (fast) {
     // threads = vpr * rpp, a multiple of 32 in [256, 512] where possible
     int rpp = 32 / gcd_int(vpr, 32);

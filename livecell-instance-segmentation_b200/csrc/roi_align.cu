@@ -25,7 +25,8 @@
 //
 // Roofline: HBM.  Algorithmic bytes fwd = 4*K*C*P*P (out) + unique feature bytes + 20*K.
 // Generic kernels (any strides / sampling ratio / pooled size) back every other configuration.
-#include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -367,6 +368,253 @@ __global__ void __launch_bounds__(NT, 4) roi_fwd_nhwc_kernel(const __grid_consta
   if (tid == 0) bulk_wait_all();
 }
 
+// ---- forward, warp items (P = 7) -----------------------------------------------------------------
+// A work item is (RoI, 64-channel group) and belongs to ONE warp: lane = channel pair, no block
+// barrier anywhere, every warp streams its own items (table build -> row walk -> 12.5 KB tile ->
+// one bulk store), so the SM always has 16 independent load streams in flight.
+//
+// x direction, "bin-dense": the two samples of a bin touch a contiguous run of <= NB columns
+// (NB = 3 for RoIs up to 14 feature px wide, 4 up to 28).  The per-sample (lo, hi, w_lo, w_hi) taps
+// are folded once per RoI into NB weights per bin, and a window row is pooled with a fixed,
+// branch-free sequence of 7*NB vector loads + 7*NB packed FMAs (no reuse bookkeeping per sample;
+// columns shared by neighbouring bins hit L1).  Wider RoIs take the per-sample path (NB = 0).
+// y direction: the distinct rows are walked once with the two-row cache (SAME / SHIFT / NEW).
+struct __align__(16) AxisTapB {
+  uint32_t off_lo, off_hi;  // BYTE offsets (already multiplied by the axis stride)
+  float w_lo, w_hi;
+};
+
+template <int P>
+struct __align__(16) WarpTables {
+  AxisTapB ys[2 * P];
+  AxisTapB xs[2 * P];
+  float4 xw[P];          // folded weights of the bin's columns xoff, xoff + sw, ... (<= 4 columns)
+  uint32_t xoff[P + 1];  // byte offset of the bin's first column
+  uint32_t ymode[2 * P];
+  int lo[2][2 * P];      // scratch: neighbour indices per axis (lo = -1: sample contributes nothing)
+  int hi[2][2 * P];
+};
+
+// Builds the tables of the warp's current RoI; returns the widest bin run in columns (0..4 -> bin
+// path with NB = max(3, run); > 4 -> per-sample path).  All 32 lanes must call.
+template <int P>
+__device__ __forceinline__ int build_tables_warp(WarpTables<P>& tb, const RoiGeom& g, const LvParam& lv, int lane) {
+  __syncwarp();  // the previous item's readers are done with the tables
+  if (lane < 2 * P) {
+    int lo, hi;
+    float wl, wh;
+    bool ok = axis_tap(sample_pos(g.sw, lane >> 1, g.bw, lane & 1, 2), lv.W, lo, hi, wl, wh);
+    tb.xs[lane] = AxisTapB{(uint32_t)(lo * lv.sw) * 4u, (uint32_t)(hi * lv.sw) * 4u, wl, wh};
+    tb.lo[0][lane] = ok ? lo : -1;
+    tb.hi[0][lane] = hi;
+    ok = axis_tap(sample_pos(g.sh, lane >> 1, g.bh, lane & 1, 2), lv.H, lo, hi, wl, wh);
+    tb.ys[lane] = AxisTapB{(uint32_t)(lo * lv.sh) * 4u, (uint32_t)(hi * lv.sh) * 4u, wl, wh};
+    tb.lo[1][lane] = ok ? lo : -1;
+    tb.hi[1][lane] = hi;
+  }
+  __syncwarp();
+  int run = 0;
+  if (lane == 31) {  // row reuse flags: a sequential scan over <= 2P samples
+    int c0 = -1, c1 = -1;
+    for (int t = 0; t < 2 * P; ++t) {
+      const int lo = tb.lo[1][t], hi = tb.hi[1][t];
+      if (lo < 0) {
+        tb.ymode[t] = 0u;
+        continue;
+      }
+      uint32_t m = (lo == c0) ? kSame : ((lo == c1) ? kShift : kNew);
+      if (hi == lo) m |= kBorder;
+      tb.ymode[t] = m | kValid;
+      c0 = lo;
+      c1 = hi;
+    }
+  } else if (lane < P) {  // fold the two samples of bin `lane` into weights over a run of columns
+    const int l0 = tb.lo[0][2 * lane], h0 = tb.hi[0][2 * lane];
+    const int l1 = tb.lo[0][2 * lane + 1], h1 = tb.hi[0][2 * lane + 1];
+    float* w = reinterpret_cast<float*>(&tb.xw[lane]);
+    w[0] = w[1] = w[2] = w[3] = 0.f;
+    int first = 0;
+    if (l0 >= 0 || l1 >= 0) {
+      const int cmin = l0 < 0 ? l1 : (l1 < 0 ? l0 : min(l0, l1));
+      const int cmax = l0 < 0 ? h1 : (l1 < 0 ? h0 : max(h0, h1));
+      first = max(min(cmin, lv.W - 4), 0);  // keep first .. first+3 inside the row (W >= 4)
+      run = cmax - first + 1;
+      if (run <= 4) {
+        if (l0 >= 0) {
+          w[l0 - first] += tb.xs[2 * lane].w_lo;
+          w[h0 - first] += tb.xs[2 * lane].w_hi;
+        }
+        if (l1 >= 0) {
+          w[l1 - first] += tb.xs[2 * lane + 1].w_lo;
+          w[h1 - first] += tb.xs[2 * lane + 1].w_hi;
+        }
+      }
+    }
+    tb.xoff[lane] = (uint32_t)(first * lv.sw) * 4u;
+  }
+  run = __reduce_max_sync(0xffffffffu, run);
+  __syncwarp();
+  return run;
+}
+
+__device__ __forceinline__ float2 ldg_f2b(const char* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+// One window row -> T[pw], x-pooled.  CSW: compile-time column stride in elements (0 = use sw).
+template <int P, int NB, int CSW>
+__device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, const char* __restrict__ row, uint32_t swb, float2 (&T)[P]) {
+  const uint32_t cs = CSW ? (uint32_t)CSW * 4u : swb;
+  if (NB > 0) {
+    float2 v[P][NB > 0 ? NB : 1];
+#pragma unroll
+    for (int pw = 0; pw < P; ++pw) {
+      const char* p = row + tb.xoff[pw];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) v[pw][j] = ldg_f2b(p + j * cs);
+    }
+#pragma unroll
+    for (int pw = 0; pw < P; ++pw) {
+      const float4 w = tb.xw[pw];
+      float2 t = __fmul2_rn(splat(w.x), v[pw][0]);
+      t = ffma2(splat(w.y), v[pw][1], t);
+      if (NB > 2) t = ffma2(splat(w.z), v[pw][2], t);
+      if (NB > 3) t = ffma2(splat(w.w), v[pw][3], t);
+      T[pw] = t;
+    }
+  } else {
+    float2 a[2 * P], b[2 * P];
+#pragma unroll
+    for (int t = 0; t < 2 * P; ++t) {
+      const AxisTapB s = tb.xs[t];  // samples that contribute nothing have offsets 0 and weights 0
+      a[t] = ldg_f2b(row + s.off_lo);
+      b[t] = ldg_f2b(row + s.off_hi);
+    }
+#pragma unroll
+    for (int pw = 0; pw < P; ++pw) T[pw] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 2 * P; ++t) {
+      const AxisTapB s = tb.xs[t];
+      if (__any_sync(0xffffffffu, s.w_lo + s.w_hi != 0.f)) {  // warp-uniform
+        T[t >> 1] = ffma2(splat(s.w_lo), a[t], T[t >> 1]);
+        T[t >> 1] = ffma2(splat(s.w_hi), b[t], T[t >> 1]);
+      }
+    }
+  }
+}
+
+// Walks the distinct rows of the window and writes this lane's two channels of the tile.
+// Every branch is warp-uniform and says so through a vote, so that ptxas keeps the uniform datapath.
+template <int P, int NB, int CSW>
+__device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, const char* __restrict__ fb, uint32_t swb,
+                                              float* __restrict__ my) {
+  constexpr int PP = P * P;
+  constexpr uint32_t kAll = 0xffffffffu;
+  float2 T0[P], T1[P], acc[P];
+#pragma unroll
+  for (int pw = 0; pw < P; ++pw) T0[pw] = T1[pw] = acc[pw] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int t = 0; t < 2 * P; ++t) {
+    const uint32_t m = tb.ymode[t];
+    if (__any_sync(kAll, m & kValid)) {
+      const uint32_t mode = m & kModeMask;
+      const AxisTapB s = tb.ys[t];
+      if (__any_sync(kAll, mode == kShift)) {
+#pragma unroll
+        for (int pw = 0; pw < P; ++pw) T0[pw] = T1[pw];
+      } else if (__any_sync(kAll, mode == kNew)) {
+        pool_row_warp<P, NB, CSW>(tb, fb + s.off_lo, swb, T0);
+      }
+      if (__any_sync(kAll, mode != kSame)) {
+        if (__any_sync(kAll, m & kBorder)) {
+#pragma unroll
+          for (int pw = 0; pw < P; ++pw) T1[pw] = T0[pw];
+        } else {
+          pool_row_warp<P, NB, CSW>(tb, fb + s.off_hi, swb, T1);
+        }
+      }
+#pragma unroll
+      for (int pw = 0; pw < P; ++pw) {
+        acc[pw] = ffma2(splat(s.w_lo), T0[pw], acc[pw]);
+        acc[pw] = ffma2(splat(s.w_hi), T1[pw], acc[pw]);
+      }
+    }
+    if (t & 1) {  // bin row complete; count = 4 for sampling_ratio 2: multiply by 0.25 is exact
+      float* o = my + (t >> 1) * P;
+#pragma unroll
+      for (int pw = 0; pw < P; ++pw) {
+        o[pw] = acc[pw].x * 0.25f;
+        o[PP + pw] = acc[pw].y * 0.25f;
+        acc[pw] = make_float2(0.f, 0.f);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_store_smem_to_global_hint(void* gdst, const void* ssrc, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+
+constexpr int kWarpChannels = 64;  // channels per warp item (lane = channel pair)
+
+template <int P, int WARPS, int CSW>
+__global__ void __launch_bounds__(WARPS * 32, 4) roi_fwd_warp_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out,
+                                                                    int groups, int stream_out) {
+  constexpr int PP = P * P;
+  constexpr int TILE = kWarpChannels * PP;  // floats
+  constexpr uint32_t kAll = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = __shfl_sync(kAll, (int)(threadIdx.x >> 5), 0);  // tells ptxas the value is warp-uniform
+  const int lane = threadIdx.x & 31;
+  float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * TILE;
+  WarpTables<P>& tb = reinterpret_cast<WarpTables<P>*>(smem_raw + sizeof(float) * WARPS * TILE)[warp];
+  float* my = tile + (size_t)(2 * lane) * PP;
+  const uint64_t pol = l2_policy_evict_first();
+  const long long items = (long long)p.K * groups;
+  const long long stride = (long long)gridDim.x * WARPS;
+
+  for (long long item = (long long)blockIdx.x * WARPS + warp; item < items; item += stride) {
+    const int k = (int)(item / groups);
+    const int cg = (int)(item - (long long)k * groups);
+    const int c0 = cg * kWarpChannels;
+    const int nch = min(kWarpChannels, p.C - c0);  // multiple of 4
+    const RoiGeom g = roi_geom(p, k);
+    const bool live = __any_sync(kAll, g.live);
+    const LvParam& lv = p.lv[live ? g.lvl : 0];
+    int run = 0;
+    if (live) run = build_tables_warp<P>(tb, g, lv, lane);
+    // the previous item's bulk store must have finished READING the tile before it is rewritten
+    if (lane == 0) bulk_wait_read_all();
+    __syncwarp();
+    if (!live) {
+#pragma unroll 7
+      for (int j = 0; j < 2 * PP; ++j) my[j] = 0.f;
+    } else {
+      // lanes past the last channel pair of a short group redo the last pair (their tile rows are not stored)
+      const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)g.b * lv.sn + c0 + min(2 * lane, nch - 2));  // sc == 1
+      const uint32_t swb = (uint32_t)lv.sw * 4u;
+      if (__all_sync(kAll, run <= 3)) roi_warp_body<P, 3, CSW>(tb, fb, swb, my);
+      else if (__all_sync(kAll, run == 4)) roi_warp_body<P, 4, CSW>(tb, fb, swb, my);
+      else roi_warp_body<P, 0, CSW>(tb, fb, swb, my);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      float* dst = out + ((size_t)k * p.C + c0) * PP;
+      const uint32_t bytes = (uint32_t)(nch * PP * sizeof(float));
+      if (stream_out) bulk_store_smem_to_global_hint(dst, tile, bytes, pol);
+      else bulk_store_smem_to_global(dst, tile, bytes);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
 // ---- backward -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
@@ -553,7 +801,7 @@ static bool fast_eligible(const RoiParams& p, const void* out) {
   for (int l = 0; l < p.L; ++l) {
     const LvParam& v = p.lv[l];
     if (v.sc != 1 || v.sw % 2 || v.sh % 2 || v.sn % 2 || !aligned_to(v.data, 8)) return false;
-    if ((long long)v.H * v.sh >= (1ll << 31) || (long long)v.W * v.sw >= (1ll << 31)) return false;
+    if ((long long)v.H * v.sh >= (1ll << 30) || (long long)v.W * v.sw >= (1ll << 30)) return false;  // 32-bit byte offsets
   }
   return true;
 }
@@ -594,6 +842,50 @@ static int launch_fast(const RoiParams& p, float* out_or_gout, cudaStream_t st) 
   return after_launch();
 }
 
+// Tuning switch read per call (A/B runs): LCR_ROI_FWD = "cta" selects the per-CTA kernel,
+// LCR_ROI_STREAM_OUT = "0" drops the evict-first hint of the output stores.
+static bool env_is(const char* name, const char* value) {
+  const char* v = getenv(name);
+  return v && strcmp(v, value) == 0;
+}
+
+template <int P, int CSW>
+static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
+  constexpr int WARPS = 4;
+  const int groups = (p.C + kWarpChannels - 1) / kWarpChannels;
+  const size_t smem = sizeof(float) * WARPS * kWarpChannels * P * P + WARPS * sizeof(WarpTables<P>);
+  const long long items = (long long)p.K * groups;
+  const long long want = (items + WARPS - 1) / WARPS;
+  const int per_sm = (int)((227 * 1024) / (smem + 1024));
+  const long long max_blocks = (long long)sm_count() * (per_sm > 4 ? 4 : (per_sm > 0 ? per_sm : 1));
+  const int blocks = (int)(want < max_blocks ? want : max_blocks);
+  auto kern = roi_fwd_warp_kernel<P, WARPS, CSW>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    configured_dev = dev;
+  }
+  kern<<<blocks, WARPS * 32, smem, st>>>(p, out, groups, env_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1);
+  return after_launch();
+}
+
+// warp-item kernel: additionally every map at least 4 columns wide
+static bool warp_eligible(const RoiParams& p) {
+  if (p.PH != 7) return false;
+  for (int l = 0; l < p.L; ++l)
+    if (p.lv[l].W < 4) return false;
+  return true;
+}
+
+static bool all_sw_equal(const RoiParams& p, long long v) {
+  for (int l = 0; l < p.L; ++l)
+    if (p.lv[l].sw != v) return false;
+  return true;
+}
+
 }  // namespace lcr
 
 using namespace lcr;
@@ -607,6 +899,10 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
   LCR_REQUIRE(out, LCR_ERR_INVALID_ARG);
   cudaStream_t st = as_stream(stream);
   if (fast_eligible(p, out)) {
+    if (warp_eligible(p) && !env_is("LCR_ROI_FWD", "cta")) {
+      if (all_sw_equal(p, 256)) return launch_fwd_warp<7, 256>(p, out, st);
+      return launch_fwd_warp<7, 0>(p, out, st);
+    }
     if (PH == 7) return launch_fast<7, 128, false>(p, out, st);
     return launch_fast<14, 32, false>(p, out, st);
   }

@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Per-kernel A/B timings at the bench workload (64 crowded 704x520 frames), CUDA events, one process.
+
+    python tools/bench_kernels.py [--frames 64] [--reps 10] [--only roi,paste,select,nms]
+
+Variants are switched through the library's tuning environment variables (read per call):
+LCR_ROI_FWD=cta|warp, LCR_ROI_STREAM_OUT=0|1, LCR_PASTE=rows16|bulk.  Every variant's output is compared with
+the first variant's (bit-exact for paste, 1e-5 relative for RoIAlign) so a faster-but-wrong kernel shows up here.
+Prints one JSON line per measurement.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench as B  # noqa: E402
+
+
+def timed(fn, reps, flush=None):
+    import torch
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return float(np.median(ms)), float(np.min(ms))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--only", default="roi,paste,select,nms,bwd")
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    import torch
+    from livecell_instance_segmentation_b200 import ops
+    from livecell_instance_segmentation_b200.pipeline import RegionConfig, RegionPipeline
+
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    F = args.frames
+    peak, _ = B.peaks()
+    obj_h, bs_h = B.make_host_inputs(F, seed0=0)
+    probs_d = torch.from_numpy(B.make_mask_probs(F * B.MAX_DET, 99)).to(dev)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    feat = torch.randn((F, B.FH, B.FW, B.C), generator=g, device=dev).permute(0, 3, 1, 2)
+    obj_d, bs_d = torch.from_numpy(obj_h).to(dev), torch.from_numpy(bs_h).to(dev)
+    pipe = RegionPipeline(RegionConfig(pre_nms_top_n=B.PRE_NMS, post_nms_top_n=B.POST_NMS, max_detections=B.MAX_DET))
+    props = pipe.proposals(obj_d, (B.IMG_H, B.IMG_W))
+    det = pipe.detections(props, bs_d)
+    n_props, n_det = int(props.counts.sum()), int(det.counts.sum())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2: cold-cache timing between reps
+
+    def emit(**kw):
+        print(json.dumps(kw), flush=True)
+
+    def setenv(env):
+        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+
+    if "roi" in only:
+        bytes_roi = 4 * n_props * B.C * 49 + F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS
+        ref = None
+        for name, env in [("cta(r01)", {"LCR_ROI_FWD": "cta"}), ("warp", {}), ("warp,no-evict-first", {"LCR_ROI_STREAM_OUT": "0"})]:
+            setenv(env)
+            out = pipe.pool(feat, props.rois)
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = out
+                err = 0.0
+            else:
+                err = float((out - ref).abs().max() / ref.abs().max())
+            med, mn = timed(lambda: pipe.pool(feat, props.rois), args.reps, flush)
+            emit(kernel="roi_align_fwd", variant=name, ms=med, ms_min=mn, GBps=bytes_roi / 1e9 / (med * 1e-3),
+                 frac=bytes_roi / 1e9 / (med * 1e-3) / peak, rel_err_vs_first=err, rois=n_props)
+            del out
+        del ref
+        setenv({})
+
+    if "bwd" in only:
+        gout = torch.randn((F * B.POST_NMS, B.C, 7, 7), generator=g, device=dev)
+        gin = torch.empty((F, B.C, B.FH, B.FW), device=dev).contiguous(memory_format=torch.channels_last)
+        bytes_bwd = 4 * n_props * B.C * 49 + 3 * F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS
+        med, mn = timed(lambda: ops.roi_align_bwd(gout, [gin], [0.25], props.rois, None, 2, False, zero_grad=True), max(3, args.reps // 2), flush)
+        emit(kernel="roi_align_bwd(+zero fill)", variant="default", ms=med, ms_min=mn, GBps=bytes_bwd / 1e9 / (med * 1e-3),
+             frac=bytes_bwd / 1e9 / (med * 1e-3) / peak)
+        del gout, gin
+
+    if "paste" in only:
+        masks = torch.empty((F * B.MAX_DET, B.IMG_H, B.IMG_W), dtype=torch.uint8, device=dev)
+        boxes_flat = det.boxes.reshape(-1, 4)
+        bytes_paste = n_det * (B.IMG_H * B.IMG_W + B.M * B.M * 4 + 16)
+        ref = None
+        for name, env in [("rows16(r01)", {"LCR_PASTE": "rows16"}), ("bulk", {})]:
+            setenv(env)
+            masks.fill_(7)
+            ops.paste_masks(probs_d, boxes_flat, B.IMG_H, B.IMG_W, 0.5, 255, valid=det.valid, out=masks)
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = masks[: 8 * B.MAX_DET].clone()
+                same = True
+            else:
+                same = bool(torch.equal(ref, masks[: 8 * B.MAX_DET]))
+            med, mn = timed(lambda: ops.paste_masks(probs_d, boxes_flat, B.IMG_H, B.IMG_W, 0.5, 255, valid=det.valid, out=masks),
+                            args.reps)
+            emit(kernel="paste", variant=name, ms=med, ms_min=mn, GBps=bytes_paste / 1e9 / (med * 1e-3),
+                 frac=bytes_paste / 1e9 / (med * 1e-3) / peak, identical_to_first=same, detections=n_det)
+        setenv({})
+        del masks
+
+    if "select" in only:
+        bytes_sel = F * (4 * B.A * B.FH * B.FW) + F * B.PRE_NMS * 28
+        fn = lambda: ops.rpn_select([obj_d], k=B.PRE_NMS, img_size=(B.IMG_H, B.IMG_W), score_thresh=0.3, min_size=10.0, strides=[4],
+                                    base=pipe.base)
+        med, mn = timed(fn, args.reps, flush)
+        emit(kernel="rpn_select", variant="default", ms=med, ms_min=mn, GBps=bytes_sel / 1e9 / (med * 1e-3),
+             frac=bytes_sel / 1e9 / (med * 1e-3) / peak)
+
+    if "nms" in only:
+        boxes, scores, _, counts = ops.rpn_select([obj_d], k=B.PRE_NMS, img_size=(B.IMG_H, B.IMG_W), score_thresh=0.3, min_size=10.0,
+                                                  strides=[4], base=pipe.base)
+        bx, ct = boxes[:, 0], counts[:, 0].contiguous()
+        med, mn = timed(lambda: ops.nms_batched(bx, None, 0.4, post_n=B.POST_NMS, counts=ct), args.reps)
+        emit(kernel="nms(64 segments x 2000)", variant="default", ms=med, ms_min=mn)
+        med, mn = timed(lambda: ops.nms_batched(bx[:1], None, 0.4, post_n=B.POST_NMS, counts=ct[:1]), args.reps)
+        emit(kernel="nms(1 segment x 2000)", variant="default", us=med * 1e3, us_min=mn * 1e3)
+        med, mn = timed(lambda: ops.nms_batched(props.boxes, bs_d, 0.5, post_n=B.MAX_DET, counts=props.counts, score_thresh=0.4), args.reps)
+        emit(kernel="det nms(64 segments x 1000, scores)", variant="default", ms=med, ms_min=mn)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,8 @@
 //                          Stops as soon as post_n boxes are kept.
 //
 // Bound: latency (N <= 2000 boxes, 20 B each) — reported in microseconds, not GB/s.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace lcr {
@@ -114,16 +116,33 @@ __global__ void __launch_bounds__(kRankThreads) nms_rank_kernel(const float4* __
 // 2. mask build.  grid (spans, row_blocks, S), 256 threads = 8 warps.
 // CTA (span sp, row block rb): rows [32rb, 32rb+32), column words [32sp, 32sp+32).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool iou_gt(const float4 a, float area_a, const float4 b, float area_b, double thr) {
+// torchvision compares the fp32 IoU with the threshold in DOUBLE.  For a float x and a double t,
+// (double)x > t  <=>  x > tf  with tf = the largest float whose double value is <= t (host side,
+// float_threshold()), so the kernel stays in fp32 — same decisions, no F2F.F64/DSETP per pair.
+// Disjoint pairs (inter == 0: IoU is 0 or NaN) can only "suppress" when tf < 0, which the
+// NEG_THR = false instantiation rules out: they skip the IEEE division (the common case by far).
+template <bool NEG_THR>
+__device__ __forceinline__ bool iou_gt(const float4 a, float area_a, const float4 b, float area_b, float tf) {
   const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
   const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
   const float width = fmaxf(__fsub_rn(right, left), 0.f), height = fmaxf(__fsub_rn(bottom, top), 0.f);
   const float inter = __fmul_rn(width, height);
+  if (!NEG_THR && !(inter > 0.f)) return false;
   const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-  return (double)iou > thr;  // NaN (0/0) compares false: never suppresses
+  return iou > tf;  // NaN (0/0) compares false: never suppresses
 }
 
-__global__ void __launch_bounds__(256) nms_mask_kernel(int stride, double thr, int use_cat, NmsWorkspace ws) {
+static float float_threshold(double thr) {
+  if (thr != thr) return nanf("");                       // x > NaN is false for every x
+  if (thr >= 3.4028234663852886e38) return INFINITY;     // nothing exceeds it
+  if (thr < -3.4028234663852886e38) return -INFINITY;    // every non-NaN IoU exceeds it
+  float tf = (float)thr;                                  // round to nearest
+  if ((double)tf > thr) tf = nextafterf(tf, -INFINITY);   // largest float <= thr
+  return tf;
+}
+
+template <bool NEG_THR>
+__global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, int use_cat, NmsWorkspace ws) {
   __shared__ float4 row_box[32];
   __shared__ float row_area[32];
   __shared__ int row_cat[32];
@@ -163,7 +182,7 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, double thr, i
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) {
         const bool hit = col_ok && (col > row0 + r) && (!use_cat || ccat == row_cat[r]) &&
-                         iou_gt(row_box[r], row_area[r], cb, carea, thr);
+                         iou_gt<NEG_THR>(row_box[r], row_area[r], cb, carea, thr);
         const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit);
         if (lane == r) my_word = word;
       }
@@ -181,14 +200,20 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, double thr, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// 3. resolve.  grid S, 32 threads.
+// 3. resolve.  grid S, one CTA of kResolveThreads per segment.
+// Warp 0 owns the serial part (greedy pass over the chunk's 32x32 diagonal block: the 32 diagonal
+// words are broadcast with shuffles up front, the dependent chain is two LOP3 per box); all warps
+// then OR the rows of the kept boxes into the `removed` bit-vector, one word per thread, every
+// thread's loads independent (one L2 round trip per chunk instead of one per kept row).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxWords = LCR_MAX_NMS_BOXES / 32;
+constexpr int kResolveThreads = 256;
 
-__global__ void __launch_bounds__(32) nms_resolve_kernel(int stride, int post_n, NmsWorkspace ws, int64_t* __restrict__ keep,
-                                                         int* __restrict__ keep_counts) {
+__global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int stride, int post_n, NmsWorkspace ws,
+                                                                      int64_t* __restrict__ keep, int* __restrict__ keep_counts) {
   __shared__ uint32_t removed[kMaxWords];
-  const int s = blockIdx.x, lane = threadIdx.x;
+  __shared__ uint32_t s_kept;
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = ws.n_valid[s];
   const int nw = ws.nw;
   const int nchunks = (n + 31) >> 5;
@@ -196,63 +221,57 @@ __global__ void __launch_bounds__(32) nms_resolve_kernel(int stride, int post_n,
   const int* order = ws.order + (size_t)s * stride;
   int64_t* out = keep + (size_t)s * post_n;
 
-  for (int w = lane; w < nchunks; w += 32) removed[w] = 0u;
+  for (int w = tid; w < nchunks; w += kResolveThreads) removed[w] = 0u;
+  __syncthreads();
   int count = 0;
-  uint32_t diag = (nchunks > 0 && lane < n) ? mask[(size_t)lane * nw] : 0u;
+  uint32_t diag = (warp == 0 && nchunks > 0 && lane < n) ? mask[(size_t)lane * nw] : 0u;
 
   for (int c = 0; c < nchunks && count < post_n; ++c) {
-    __syncwarp();
     const int row0 = c << 5;
-    // prefetch the next chunk's diagonal word (address is data-independent)
-    const int nrow = row0 + 32 + lane;
-    const uint32_t diag_next = (c + 1 < nchunks && nrow < n) ? mask[(size_t)nrow * nw + (c + 1)] : 0u;
-
-    const int left = n - row0;
-    const uint32_t in_range = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
-    uint32_t alive = ~removed[c] & in_range;
-
-    // speculative loads of the first word block of every row that may still be kept
-    const int w0 = c + 1 + lane;
-    uint32_t rows0[32];
+    if (warp == 0) {
+      // prefetch the next chunk's diagonal word (address is data-independent)
+      const int nrow = row0 + 32 + lane;
+      const uint32_t diag_next = (c + 1 < nchunks && nrow < n) ? mask[(size_t)nrow * nw + (c + 1)] : 0u;
+      const int left = n - row0;
+      const uint32_t in_range = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+      uint32_t alive = ~removed[c] & in_range;
+      uint32_t d[32];
 #pragma unroll
-    for (int b = 0; b < 32; ++b)
-      rows0[b] = (((alive >> b) & 1u) && w0 < nchunks) ? mask[(size_t)(row0 + b) * nw + w0] : 0u;
-
-    // serial part: greedy over the chunk's 32x32 diagonal block, in registers
-    uint32_t kept = 0u;
+      for (int b = 0; b < 32; ++b) d[b] = __shfl_sync(0xFFFFFFFFu, diag, b);
+      uint32_t kept = 0u;
 #pragma unroll
-    for (int b = 0; b < 32; ++b) {
-      const uint32_t d = __shfl_sync(0xFFFFFFFFu, diag, b);
-      if ((alive >> b) & 1u) {
-        kept |= 1u << b;
-        alive &= ~d;
+      for (int b = 0; b < 32; ++b) {
+        if ((alive >> b) & 1u) {
+          kept |= 1u << b;
+          alive &= ~d[b];
+        }
+      }
+      if ((kept >> lane) & 1u) {  // emit the kept boxes of this chunk in order
+        const int pos = count + __popc(kept & ((1u << lane) - 1u));
+        if (pos < post_n) out[pos] = (int64_t)order[row0 + lane];
+      }
+      if (lane == 0) s_kept = kept;
+      diag = diag_next;
+    }
+    __syncthreads();
+    const uint32_t kept = s_kept;
+    count += __popc(kept);
+    if (count < post_n) {  // block-uniform
+      for (int w = c + 1 + tid; w < nchunks; w += kResolveThreads) {
+        // all 32 row words are loaded unconditionally (independent loads: one L2 round trip, not one per
+        // kept row) and selected afterwards; rows past n are clamped (their kept bit is 0)
+        uint32_t v[32];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) v[b] = __ldcg(mask + (size_t)min(row0 + b, n - 1) * nw + w);
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) acc |= ((kept >> b) & 1u) ? v[b] : 0u;
+        removed[w] |= acc;
       }
     }
-
-    // emit kept boxes of this chunk in order
-    if ((kept >> lane) & 1u) {
-      const int pos = count + __popc(kept & ((1u << lane) - 1u));
-      if (pos < post_n) out[pos] = (int64_t)order[row0 + lane];
-    }
-    count += __popc(kept);
-
-    // propagate the kept rows into `removed`
-    if (w0 < nchunks) {
-      uint32_t acc = 0u;
-#pragma unroll
-      for (int b = 0; b < 32; ++b) acc |= ((kept >> b) & 1u) ? rows0[b] : 0u;
-      removed[w0] |= acc;
-    }
-    for (int w = w0 + 32; w < nchunks; w += 32) {
-      uint32_t acc = 0u;
-#pragma unroll 8
-      for (int b = 0; b < 32; ++b)
-        if ((kept >> b) & 1u) acc |= mask[(size_t)(row0 + b) * nw + w];
-      removed[w] |= acc;
-    }
-    diag = diag_next;
+    __syncthreads();
   }
-  if (lane == 0) keep_counts[s] = min(count, post_n);
+  if (tid == 0) keep_counts[s] = min(count, post_n);
 }
 
 }  // namespace lcr
@@ -287,10 +306,12 @@ extern "C" int lcr_nms_f32(const float* boxes, const float* scores, const int* c
   const int row_blocks = (stride + 31) / 32;
   const int spans = (ws.nw + 31) / 32;
   dim3 g2(spans, row_blocks, S);
-  nms_mask_kernel<<<g2, 256, 0, st>>>(stride, iou_threshold, category != nullptr, ws);
+  const float tf = float_threshold(iou_threshold);
+  if (tf < 0.f) nms_mask_kernel<true><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, ws);
+  else nms_mask_kernel<false><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, ws);
   rc = after_launch();
   if (rc != LCR_OK) return rc;
 
-  nms_resolve_kernel<<<S, 32, 0, st>>>(stride, post_n, ws, keep, keep_counts);
+  nms_resolve_kernel<<<S, kResolveThreads, 0, st>>>(stride, post_n, ws, keep, keep_counts);
   return after_launch();
 }

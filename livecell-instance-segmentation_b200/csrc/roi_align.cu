@@ -461,13 +461,14 @@ __device__ __forceinline__ float2 ldg_f2b(const char* p) { return __ldg(reinterp
 
 // One window row -> T[pw], x-pooled.  CSW: compile-time column stride in elements (0 = use sw).
 template <int P, int NB, int CSW>
-__device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, const char* __restrict__ row, uint32_t swb, float2 (&T)[P]) {
+__device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, const uint32_t (&xo)[P], const char* __restrict__ row,
+                                              uint32_t swb, float2 (&T)[P]) {
   const uint32_t cs = CSW ? (uint32_t)CSW * 4u : swb;
   if (NB > 0) {
     float2 v[P][NB > 0 ? NB : 1];
 #pragma unroll
     for (int pw = 0; pw < P; ++pw) {
-      const char* p = row + tb.xoff[pw];
+      const char* p = row + xo[pw];
 #pragma unroll
       for (int j = 0; j < NB; ++j) v[pw][j] = ldg_f2b(p + j * cs);
     }
@@ -509,8 +510,18 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, const cha
   constexpr int PP = P * P;
   constexpr uint32_t kAll = 0xffffffffu;
   float2 T0[P], T1[P], acc[P];
+  uint32_t xo[P];  // bin column offsets stay in registers for the whole RoI
 #pragma unroll
-  for (int pw = 0; pw < P; ++pw) T0[pw] = T1[pw] = acc[pw] = make_float2(0.f, 0.f);
+  for (int pw = 0; pw < P; ++pw) {
+    T0[pw] = T1[pw] = acc[pw] = make_float2(0.f, 0.f);
+    xo[pw] = NB > 0 ? tb.xoff[pw] : 0u;
+  }
+  // Tile stores without bank conflicts: the lane's channel rows start 98 words apart, so lanes l and l+16
+  // share banks; the upper half-warp therefore stores its odd channel while the lower stores its even one
+  // (49 words = 17 banks apart) and vice versa.
+  const bool lower = (threadIdx.x & 16) == 0;
+  float* const o_a = my + (lower ? 0 : PP);
+  float* const o_b = my + (lower ? PP : 0);
 #pragma unroll 1
   for (int t = 0; t < 2 * P; ++t) {
     const uint32_t m = tb.ymode[t];
@@ -521,14 +532,14 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, const cha
 #pragma unroll
         for (int pw = 0; pw < P; ++pw) T0[pw] = T1[pw];
       } else if (__any_sync(kAll, mode == kNew)) {
-        pool_row_warp<P, NB, CSW>(tb, fb + s.off_lo, swb, T0);
+        pool_row_warp<P, NB, CSW>(tb, xo, fb + s.off_lo, swb, T0);
       }
       if (__any_sync(kAll, mode != kSame)) {
         if (__any_sync(kAll, m & kBorder)) {
 #pragma unroll
           for (int pw = 0; pw < P; ++pw) T1[pw] = T0[pw];
         } else {
-          pool_row_warp<P, NB, CSW>(tb, fb + s.off_hi, swb, T1);
+          pool_row_warp<P, NB, CSW>(tb, xo, fb + s.off_hi, swb, T1);
         }
       }
 #pragma unroll
@@ -538,11 +549,12 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, const cha
       }
     }
     if (t & 1) {  // bin row complete; count = 4 for sampling_ratio 2: multiply by 0.25 is exact
-      float* o = my + (t >> 1) * P;
+      const int o = (t >> 1) * P;
 #pragma unroll
       for (int pw = 0; pw < P; ++pw) {
-        o[pw] = acc[pw].x * 0.25f;
-        o[PP + pw] = acc[pw].y * 0.25f;
+        const float e = acc[pw].x * 0.25f, f = acc[pw].y * 0.25f;
+        o_a[o + pw] = lower ? e : f;
+        o_b[o + pw] = lower ? f : e;
         acc[pw] = make_float2(0.f, 0.f);
       }
     }
@@ -564,7 +576,7 @@ constexpr int kWarpChannels = 64;  // channels per warp item (lane = channel pai
 
 template <int P, int WARPS, int CSW>
 __global__ void __launch_bounds__(WARPS * 32, 4) roi_fwd_warp_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out,
-                                                                    int groups, int stream_out) {
+                                                                    int groups, int stream_out, int ipw) {
   constexpr int PP = P * P;
   constexpr int TILE = kWarpChannels * PP;  // floats
   constexpr uint32_t kAll = 0xffffffffu;
@@ -576,9 +588,16 @@ __global__ void __launch_bounds__(WARPS * 32, 4) roi_fwd_warp_kernel(const __gri
   float* my = tile + (size_t)(2 * lane) * PP;
   const uint64_t pol = l2_policy_evict_first();
   const long long items = (long long)p.K * groups;
-  const long long stride = (long long)gridDim.x * WARPS;
+  // Work order.  ipw > 0: CTA b owns the WARPS*ipw consecutive items starting at b*WARPS*ipw (warp w takes
+  // every WARPS-th of them); the grid covers all items and the hardware launches CTAs in index order as SMs
+  // drain, so the RoIs in flight are always neighbours in the list (one or two frames: their feature maps
+  // stay L2-resident).  ipw == 0: persistent grid with a static stride (kept for A/B runs; warps drift
+  // apart by many frames and the maps are re-read from HBM).
+  const long long first = ipw > 0 ? (long long)blockIdx.x * WARPS * ipw + warp : (long long)blockIdx.x * WARPS + warp;
+  const long long last = ipw > 0 ? min(items, ((long long)blockIdx.x + 1) * WARPS * ipw) : items;
+  const long long stride = ipw > 0 ? WARPS : (long long)gridDim.x * WARPS;
 
-  for (long long item = (long long)blockIdx.x * WARPS + warp; item < items; item += stride) {
+  for (long long item = first; item < last; item += stride) {
     const int k = (int)(item / groups);
     const int cg = (int)(item - (long long)k * groups);
     const int c0 = cg * kWarpChannels;
@@ -855,10 +874,18 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
   const int groups = (p.C + kWarpChannels - 1) / kWarpChannels;
   const size_t smem = sizeof(float) * WARPS * kWarpChannels * P * P + WARPS * sizeof(WarpTables<P>);
   const long long items = (long long)p.K * groups;
-  const long long want = (items + WARPS - 1) / WARPS;
-  const int per_sm = (int)((227 * 1024) / (smem + 1024));
-  const long long max_blocks = (long long)sm_count() * (per_sm > 4 ? 4 : (per_sm > 0 ? per_sm : 1));
-  const int blocks = (int)(want < max_blocks ? want : max_blocks);
+  int ipw = 2;  // items per warp per CTA
+  if (const char* v = getenv("LCR_ROI_IPW")) ipw = atoi(v);
+  long long want = (items + WARPS - 1) / WARPS;
+  if (ipw > 0) {
+    want = (items + (long long)WARPS * ipw - 1) / ((long long)WARPS * ipw);
+  } else {
+    const int per_sm = (int)((227 * 1024) / (smem + 1024));
+    const long long max_blocks = (long long)sm_count() * (per_sm > 4 ? 4 : (per_sm > 0 ? per_sm : 1));
+    want = want < max_blocks ? want : max_blocks;
+  }
+  LCR_REQUIRE(want < (1ll << 31), LCR_ERR_CAPACITY);
+  const int blocks = (int)want;
   auto kern = roi_fwd_warp_kernel<P, WARPS, CSW>;
   static thread_local int configured_dev = -1;
   int dev = 0;
@@ -868,7 +895,7 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e);
     configured_dev = dev;
   }
-  kern<<<blocks, WARPS * 32, smem, st>>>(p, out, groups, env_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1);
+  kern<<<blocks, WARPS * 32, smem, st>>>(p, out, groups, env_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1, ipw);
   return after_launch();
 }
 

@@ -21,6 +21,9 @@
 //
 // Tie rule (torch.topk leaves it unspecified): (key desc, flat index asc); NaN ranks highest.
 #include <cooperative_groups.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -53,6 +56,8 @@ struct SelParams {
   unsigned long long* cand;    // [S][k]
   unsigned long long* sorted;  // [S][k]
   unsigned int* counters;      // [S]
+  unsigned long long* pre_cand;  // [S][kPreCap] threshold-first survivors (NULL: fast path off)
+  unsigned int* pre_count;     // [S][2]: survivors, NaNs
   int region_bytes;            // shared-memory bytes after the histogram (key cache / candidate copy)
 };
 
@@ -69,7 +74,8 @@ __device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t bin, bool acti
   }
 }
 
-// Block-wide exclusive prefix sum (blockDim.x == kSelThreads); returns the block total in `total`.
+// Block-wide exclusive prefix sum (blockDim.x == NT); returns the block total in `total`.
+template <int NT = 512>
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   uint32_t incl = v;
@@ -83,7 +89,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
   __syncthreads();
   uint32_t woff = 0, tot = 0;
 #pragma unroll
-  for (int w = 0; w < kSelThreads / 32; ++w) {
+  for (int w = 0; w < NT / 32; ++w) {
     const uint32_t t = s_warp[w];
     if (w < warp) woff += t;
     tot += t;
@@ -135,11 +141,180 @@ __device__ __forceinline__ void cluster_select_bin(cg::cluster_group& cluster, u
   cluster.sync();  // remote reads done: histograms may be reused
 }
 
+// Ordered epilogue over `take` candidates sorted by (key desc, flat index asc): score threshold,
+// anchor generate/gather, optional delta decode, clip, min-size filter, ordered compaction,
+// device-side count (src/utils/proposal_utils.py:21-29,43-52; TV:models/detection/rpn.py:277-287).
+template <int NT, bool SORTED_IN_SMEM>
+__device__ __forceinline__ void ordered_epilogue(const SelParams& p, int seg, int b, int l, const unsigned long long* sorted,
+                                                 int take, uint32_t* s_warp) {
+  const SelLevel& lv = p.lv[l];
+  const int A = p.A, P = lv.h * lv.w, n = A * P;
+  const float* obj = lv.obj + (size_t)b * n;
+  const int tid = threadIdx.x;
+  const int per = (take + NT - 1) / NT;
+  const int jb = min(take, tid * per), je = min(take, jb + per);
+  const int W = lv.w;
+
+  auto eval = [&](int j, float4& box, float& score, uint32_t& flat) -> bool {
+    const unsigned long long v = SORTED_IN_SMEM ? sorted[j] : __ldcg(sorted + j);
+    flat = 0xFFFFFFFFu - (uint32_t)(v & 0xFFFFFFFFull);
+    const int a = (int)(flat % (uint32_t)A), pos = (int)(flat / (uint32_t)A);
+    score = sigmoid_f32(__ldg(obj + (size_t)a * P + pos));
+    const bool pass = p.score_strict ? (score > p.score_thresh) : (score >= p.score_thresh);
+    if (!pass) return false;
+    if (lv.anchors) {
+      box = __ldg(reinterpret_cast<const float4*>(lv.anchors) + flat);
+    } else {
+      const int y = pos / W, x = pos - y * W;
+      const float sx = __fmul_rn((float)x, (float)lv.stride), sy = __fmul_rn((float)y, (float)lv.stride);
+      const float* ba = p.base[l] + a * 4;
+      box = make_float4(__fadd_rn(sx, ba[0]), __fadd_rn(sy, ba[1]), __fadd_rn(sx, ba[2]), __fadd_rn(sy, ba[3]));
+    }
+    if (lv.deltas) {
+      const float* d = lv.deltas + (size_t)b * 4 * n + (size_t)(a * 4) * P + pos;
+      box = decode_one(make_float4(__ldg(d), __ldg(d + P), __ldg(d + 2 * (size_t)P), __ldg(d + 3 * (size_t)P)), box, p.dec);
+    }
+    box.x = clampf(box.x, 0.f, p.img_w);
+    box.z = clampf(box.z, 0.f, p.img_w);
+    box.y = clampf(box.y, 0.f, p.img_h);
+    box.w = clampf(box.w, 0.f, p.img_h);
+    return (__fsub_rn(box.z, box.x) >= p.min_size) && (__fsub_rn(box.w, box.y) >= p.min_size);
+  };
+
+  uint32_t cnt = 0;
+  for (int j = jb; j < je; ++j) {
+    float4 box;
+    float score;
+    uint32_t flat;
+    cnt += eval(j, box, score, flat) ? 1u : 0u;
+  }
+  uint32_t total;
+  uint32_t o = block_exclusive_scan<NT>(cnt, s_warp, total);
+  float4* out_boxes = reinterpret_cast<float4*>(p.boxes) + (size_t)seg * p.k;
+  float* out_scores = p.scores + (size_t)seg * p.k;
+  long long* out_index = p.index + (size_t)seg * p.k;
+  for (int j = jb; j < je; ++j) {
+    float4 box;
+    float score;
+    uint32_t flat;
+    if (eval(j, box, score, flat)) {
+      out_boxes[o] = box;
+      out_scores[o] = score;
+      out_index[o] = (long long)flat;
+      ++o;
+    }
+  }
+  if (tid == 0) p.counts[seg] = (int)total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Threshold-first fast path.
+// top-k followed by "score > thr" keeps a PREFIX of the sorted top-k, so it equals: drop everything
+// that fails the threshold, then take the top-k of the survivors (NaN scores, which rank first in
+// torch.topk but fail the threshold, are the one exception and send the segment to the general
+// kernel).  On a real objectness map only a few thousand of the 205 920 anchors pass 0.3, so:
+//   1. rpn_prefilter_kernel — one streaming pass over the logits at HBM speed (8 independent loads
+//      per thread, one compare per element; the exact sigmoid is evaluated only inside a narrow band
+//      around logit(thr)); survivors are appended as 64-bit (key, ~index) with warp-aggregated atomics;
+//   2. rpn_sortfilter_kernel — one CTA per segment: survivors (<= kPreCap) into shared memory,
+//      bitonic sort on (key desc, index asc), first min(k, M) through the ordered epilogue.
+// Segments with more than kPreCap survivors (low thresholds, e.g. the training path's 0.01) or a NaN
+// are left to the general cluster kernel, which returns immediately for the others.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPreCap = 8192;
+constexpr int kPreThreads = 256;
+constexpr int kPreEPT = 8;
+constexpr int kSortThreads = 1024;
+
+__global__ void __launch_bounds__(kPreThreads) rpn_prefilter_kernel(const __grid_constant__ SelParams p, float band_lo, float band_hi) {
+  const int seg = blockIdx.y;
+  const int b = seg / p.L, l = seg - b * p.L;
+  const SelLevel& lv = p.lv[l];
+  const int A = p.A, P = lv.h * lv.w, n = A * P;
+  const int m0 = blockIdx.x * (kPreThreads * kPreEPT) + threadIdx.x;
+  if (blockIdx.x * (kPreThreads * kPreEPT) >= n) return;
+  const float* obj = lv.obj + (size_t)b * n;
+  unsigned long long* cand = p.pre_cand + (size_t)seg * kPreCap;
+  float v[kPreEPT];
+#pragma unroll
+  for (int j = 0; j < kPreEPT; ++j) {
+    const int m = m0 + j * kPreThreads;
+    v[j] = m < n ? __ldg(obj + m) : -INFINITY;   // -inf never passes and is not NaN
+  }
+#pragma unroll
+  for (int j = 0; j < kPreEPT; ++j) {
+    const int m = m0 + j * kPreThreads;
+    const float x = v[j];
+    bool pass = x > band_hi;   // (padding lanes hold -inf: never above the band)
+    if (!pass && x >= band_lo && m < n) {
+      const float s = sigmoid_f32(x);
+      pass = p.score_strict ? (s > p.score_thresh) : (s >= p.score_thresh);
+    }
+    const bool isnan_ = (x != x);
+    const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass);
+    const unsigned nm = __ballot_sync(0xFFFFFFFFu, isnan_);
+    if (nm && lane_id() == 0) atomicAdd(&p.pre_count[2 * seg + 1], (uint32_t)__popc(nm));
+    if (pm) {
+      uint32_t pos0 = 0;
+      if (lane_id() == 0) pos0 = atomicAdd(&p.pre_count[2 * seg], (uint32_t)__popc(pm));
+      pos0 = __shfl_sync(0xFFFFFFFFu, pos0, 0);
+      if (pass) {
+        const uint32_t pos = pos0 + __popc(pm & ((1u << lane_id()) - 1u));
+        if (pos < (uint32_t)kPreCap) {
+          const int a = m / P, pp = m - a * P;
+          const uint32_t flat = (uint32_t)(pp * A + a);
+          cand[pos] = ((unsigned long long)make_key(x, p.topk_on_sigmoid) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ bool fast_path_done(const SelParams& p, int seg) {
+  return p.pre_count && p.pre_count[2 * seg] <= (uint32_t)kPreCap && p.pre_count[2 * seg + 1] == 0u;
+}
+
+__global__ void __launch_bounds__(kSortThreads) rpn_sortfilter_kernel(const __grid_constant__ SelParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned long long* s = reinterpret_cast<unsigned long long*>(smem);
+  __shared__ uint32_t s_warp[kSortThreads / 32];
+  const int seg = blockIdx.x;
+  if (!fast_path_done(p, seg)) return;  // block-uniform: the general kernel owns this segment
+  const int b = seg / p.L, l = seg - b * p.L;
+  const SelLevel& lv = p.lv[l];
+  const int n = p.A * lv.h * lv.w;
+  const int M = (int)p.pre_count[2 * seg];
+  const int tid = threadIdx.x;
+  int SZ = 32;
+  while (SZ < M) SZ <<= 1;
+  const unsigned long long* cand = p.pre_cand + (size_t)seg * kPreCap;
+  for (int i = tid; i < SZ; i += kSortThreads) s[i] = i < M ? __ldcg(cand + i) : 0ull;  // 0 sorts last
+  // bitonic sort, descending
+  for (int size = 2; size <= SZ; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = tid; t < (SZ >> 1); t += kSortThreads) {
+        const int i = 2 * t - (t & (stride - 1));
+        const int j = i + stride;
+        const unsigned long long x = s[i], y = s[j];
+        const bool desc = (i & size) == 0;
+        if ((x < y) == desc) {
+          s[i] = y;
+          s[j] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  ordered_epilogue<kSortThreads, true>(p, seg, b, l, s, min(M, min(p.k, n)), s_warp);
+}
+
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSelThreads, 1)
     rpn_select_kernel(const __grid_constant__ SelParams p) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int seg = blockIdx.x / kCluster;
+  if (p.pre_count && p.pre_count[2 * seg] <= 8192u && p.pre_count[2 * seg + 1] == 0u) return;  // cluster-uniform: fast path did it
   const int b = seg / p.L, l = seg - b * p.L;
   const SelLevel& lv = p.lv[l];
   const int A = p.A, P = lv.h * lv.w, n = A * P;
@@ -290,60 +465,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kSelThreads, 
   if (rank != 0) return;  // no DSMEM access after this point
 
   // ---- ordered epilogue (CTA 0): threshold, box, clip, min-size, compaction ---------------------
-  const int per = (kk + kSelThreads - 1) / kSelThreads;  // <= 16
-  const int jb = min(kk, tid * per), je = min(kk, jb + per);
-  const int W = lv.w;
-
-  auto eval = [&](int j, float4& box, float& score, uint32_t& flat) -> bool {
-    const unsigned long long v = __ldcg(sorted + j);
-    flat = 0xFFFFFFFFu - (uint32_t)(v & 0xFFFFFFFFull);
-    const int a = (int)(flat % (uint32_t)A), pos = (int)(flat / (uint32_t)A);
-    score = sigmoid_f32(__ldg(sv.obj + (size_t)a * P + pos));
-    const bool pass = p.score_strict ? (score > p.score_thresh) : (score >= p.score_thresh);
-    if (!pass) return false;
-    if (lv.anchors) {
-      box = __ldg(reinterpret_cast<const float4*>(lv.anchors) + flat);
-    } else {
-      const int y = pos / W, x = pos - y * W;
-      const float sx = __fmul_rn((float)x, (float)lv.stride), sy = __fmul_rn((float)y, (float)lv.stride);
-      const float* ba = p.base[l] + a * 4;
-      box = make_float4(__fadd_rn(sx, ba[0]), __fadd_rn(sy, ba[1]), __fadd_rn(sx, ba[2]), __fadd_rn(sy, ba[3]));
-    }
-    if (lv.deltas) {
-      const float* d = lv.deltas + (size_t)b * 4 * n + (size_t)(a * 4) * P + pos;
-      box = decode_one(make_float4(__ldg(d), __ldg(d + P), __ldg(d + 2 * (size_t)P), __ldg(d + 3 * (size_t)P)), box, p.dec);
-    }
-    box.x = clampf(box.x, 0.f, p.img_w);
-    box.z = clampf(box.z, 0.f, p.img_w);
-    box.y = clampf(box.y, 0.f, p.img_h);
-    box.w = clampf(box.w, 0.f, p.img_h);
-    return (__fsub_rn(box.z, box.x) >= p.min_size) && (__fsub_rn(box.w, box.y) >= p.min_size);
-  };
-
-  uint32_t cnt = 0;
-  for (int j = jb; j < je; ++j) {
-    float4 box;
-    float score;
-    uint32_t flat;
-    cnt += eval(j, box, score, flat) ? 1u : 0u;
-  }
-  uint32_t total;
-  uint32_t o = block_exclusive_scan(cnt, s_warp, total);
-  float4* out_boxes = reinterpret_cast<float4*>(p.boxes) + (size_t)seg * p.k;
-  float* out_scores = p.scores + (size_t)seg * p.k;
-  long long* out_index = p.index + (size_t)seg * p.k;
-  for (int j = jb; j < je; ++j) {
-    float4 box;
-    float score;
-    uint32_t flat;
-    if (eval(j, box, score, flat)) {
-      out_boxes[o] = box;
-      out_scores[o] = score;
-      out_index[o] = (long long)flat;
-      ++o;
-    }
-  }
-  if (tid == 0) p.counts[seg] = (int)total;
+  ordered_epilogue<kSelThreads, false>(p, seg, b, l, p.sorted + (size_t)seg * p.k, kk, s_warp);
 }
 
 static size_t select_ws_layout(int S, int k, void* base, SelParams* p) {
@@ -356,11 +478,15 @@ static size_t select_ws_layout(int S, int k, void* base, SelParams* p) {
   const size_t o_cand = take((size_t)S * k * 8);
   const size_t o_sorted = take((size_t)S * k * 8);
   const size_t o_cnt = take((size_t)S * 4);
+  const size_t o_pcnt = take((size_t)S * 8);
+  const size_t o_pcand = take((size_t)S * 8192 * 8);
   if (p) {
     char* bp = static_cast<char*>(base);
     p->cand = reinterpret_cast<unsigned long long*>(bp + o_cand);
     p->sorted = reinterpret_cast<unsigned long long*>(bp + o_sorted);
     p->counters = reinterpret_cast<unsigned int*>(bp + o_cnt);
+    p->pre_count = reinterpret_cast<unsigned int*>(bp + o_pcnt);
+    p->pre_cand = reinterpret_cast<unsigned long long*>(bp + o_pcand);
   }
   return off;
 }
@@ -425,6 +551,39 @@ extern "C" int lcr_rpn_select_f32(const LcrRpnLevel* levels_host, int L, int B, 
     configured_dev = dev;
     configured_smem = smem;
   }
-  rpn_select_kernel<<<S * kCluster, kSelThreads, smem, as_stream(stream)>>>(p);
+  cudaStream_t st = as_stream(stream);
+  const char* mode = getenv("LCR_SELECT");  // tuning switch for A/B runs: "general" disables the threshold-first path
+  const bool fast = !(mode && strcmp(mode, "general") == 0);
+  if (fast) {
+    // logit band outside which the threshold decision needs no sigmoid: logit(thr) -+ 0.01 (thr away from 0 and 1)
+    float lo = -INFINITY, hi = INFINITY;
+    const double t = (double)cfg->score_thresh;
+    if (t > 1e-4 && t < 1.0 - 1e-4) {
+      const double x = log(t / (1.0 - t));
+      lo = (float)(x - 0.01);
+      hi = (float)(x + 0.01);
+    }
+    cudaError_t e = cudaMemsetAsync(p.pre_count, 0, (size_t)S * 8, st);
+    if (e != cudaSuccess) return cuda_status(e);
+    int max_n = 0;
+    for (int l = 0; l < L; ++l) max_n = max_n > levels_host[l].h * levels_host[l].w * cfg->num_anchors ? max_n : levels_host[l].h * levels_host[l].w * cfg->num_anchors;
+    dim3 g1((max_n + kPreThreads * kPreEPT - 1) / (kPreThreads * kPreEPT), S);
+    rpn_prefilter_kernel<<<g1, kPreThreads, 0, st>>>(p, lo, hi);
+    int rc = after_launch();
+    if (rc != LCR_OK) return rc;
+    static thread_local int sort_dev = -1;
+    if (sort_dev != dev) {
+      e = cudaFuncSetAttribute(rpn_sortfilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreCap * 8);
+      if (e != cudaSuccess) return cuda_status(e);
+      sort_dev = dev;
+    }
+    rpn_sortfilter_kernel<<<S, kSortThreads, kPreCap * 8, st>>>(p);
+    rc = after_launch();
+    if (rc != LCR_OK) return rc;
+  } else {
+    p.pre_count = nullptr;
+    p.pre_cand = nullptr;
+  }
+  rpn_select_kernel<<<S * kCluster, kSelThreads, smem, st>>>(p);
   return after_launch();
 }

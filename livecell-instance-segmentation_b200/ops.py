@@ -289,15 +289,22 @@ def _dense(f: torch.Tensor) -> bool:
 
 
 def roi_align_fwd(feats: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
-                  roi_level: Optional[torch.Tensor], output_size, sampling_ratio: int, aligned: bool) -> torch.Tensor:
+                  roi_level: Optional[torch.Tensor], output_size, sampling_ratio: int, aligned: bool,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a9/a11 — RoIAlign forward over one or several levels.  feats: logical [N,C,H,W] fp32 tensors
-    (NCHW-contiguous or channels_last; other stridings are copied).  rois [K,5]."""
+    (NCHW-contiguous or channels_last; other stridings are copied).  rois [K,5].  `out`: optional
+    caller-owned contiguous fp32 buffer of at least K*C*PH*PW elements (a serving loop reuses it)."""
     feats = [f if (f.dtype == torch.float32 and _dense(f)) else _f32c(f) for f in feats]
     r = _f32c(rois).reshape(-1, 5)
     _need_cuda(r, roi_level, *feats)
     PH, PW = (output_size, output_size) if isinstance(output_size, int) else output_size
     K, Cc = r.shape[0], feats[0].shape[1]
-    out = torch.empty((K, Cc, PH, PW), dtype=torch.float32, device=r.device)
+    if out is None:
+        out = torch.empty((K, Cc, PH, PW), dtype=torch.float32, device=r.device)
+    else:
+        if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() < K * Cc * PH * PW or out.device != r.device:
+            raise _lib.LcrError("roi_align_fwd: out must be a contiguous fp32 CUDA buffer of at least K*C*PH*PW elements")
+        out = out.reshape(-1)[: K * Cc * PH * PW].view(K, Cc, PH, PW)
     if K == 0:
         return out
     lvl = None if roi_level is None else roi_level.to(torch.int32).contiguous()

@@ -168,3 +168,29 @@ def test_error_paths(ops):
     with pytest.raises(LcrError):
         ops.rpn_select([obj.cpu()], k=10, img_size=(16, 16), score_thresh=0.0, min_size=0.0, strides=[4],
                        base=ops.base_anchors())                      # CPU tensor: no fallback
+
+
+def test_threshold_first_path_boundaries(ops, oracle):
+    """The threshold-first path (prefilter + in-CTA sort) and the general cluster kernel must agree with the
+    oracle on both sides of the survivor capacity (8192), and for logits inside the band around logit(thr)
+    where the prefilter evaluates the exact sigmoid."""
+    base = oracle.base_anchors()
+    rng = np.random.RandomState(11)
+    for n_pass in (8191, 8192, 8193, 9000):
+        obj = rng.normal(-6, 0.5, size=(1, 9, 40, 48)).astype(np.float32)
+        flat = obj.reshape(-1)
+        hot = rng.choice(flat.size, n_pass, replace=False)
+        flat[hot] = rng.permutation(np.linspace(1.0, 9.0, n_pass)).astype(np.float32)    # distinct scores
+        check_against_oracle(ops, oracle, obj, 2000, 0.3, 0.0, 160, 192, base)
+    # logits within +-1e-5 of logit(0.3) = -0.8472979: sigmoid lands on both sides of 0.3f
+    obj = np.full((1, 9, 20, 24), -7.0, np.float32)
+    flat = obj.reshape(-1)
+    centre = np.float32(np.log(0.3 / 0.7))
+    near = centre + (np.arange(-200, 200).astype(np.float32) * np.float32(1e-7))
+    flat[rng.choice(flat.size, near.size, replace=False)] = near
+    for strict in (True, False):
+        check_against_oracle(ops, oracle, obj, 300, 0.3, 0.0, 80, 96, base, strict=strict)
+    # fewer survivors than k: everything that passes comes out, sorted
+    obj = rng.normal(-5, 0.3, size=(2, 9, 20, 24)).astype(np.float32)
+    obj.reshape(2, -1)[:, rng.choice(9 * 20 * 24, 37, replace=False)] = rng.uniform(0, 6, size=37).astype(np.float32)
+    check_against_oracle(ops, oracle, obj, 250, 0.3, 0.0, 80, 96, base)

@@ -68,14 +68,15 @@ def main():
         print(json.dumps(kw), flush=True)
 
     def setenv(env):
-        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD"):
+        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT"):
             os.environ.pop(k, None)
         os.environ.update(env)
 
     if "roi" in only:
         bytes_roi = 4 * n_props * B.C * 49 + F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS
         ref = None
-        for name, env in [("cta(r01)", {"LCR_ROI_FWD": "cta"}), ("warp", {}), ("warp,no-evict-first", {"LCR_ROI_STREAM_OUT": "0"})]:
+        for name, env in [("cta(r01)", {"LCR_ROI_FWD": "cta"}), ("warp,persistent", {"LCR_ROI_IPW": "0"}), ("warp,ipw1", {"LCR_ROI_IPW": "1"}),
+                          ("warp,ipw2", {"LCR_ROI_IPW": "2"}), ("warp,ipw3", {"LCR_ROI_IPW": "3"})]:
             setenv(env)
             out = pipe.pool(feat, props.rois)
             torch.cuda.synchronize()
@@ -126,9 +127,22 @@ def main():
         bytes_sel = F * (4 * B.A * B.FH * B.FW) + F * B.PRE_NMS * 28
         fn = lambda: ops.rpn_select([obj_d], k=B.PRE_NMS, img_size=(B.IMG_H, B.IMG_W), score_thresh=0.3, min_size=10.0, strides=[4],
                                     base=pipe.base)
-        med, mn = timed(fn, args.reps, flush)
-        emit(kernel="rpn_select", variant="default", ms=med, ms_min=mn, GBps=bytes_sel / 1e9 / (med * 1e-3),
-             frac=bytes_sel / 1e9 / (med * 1e-3) / peak)
+        ref = None
+        for name, env in [("general(r01)", {"LCR_SELECT": "general"}), ("threshold-first", {})]:
+            setenv(env)
+            outs = fn()
+            torch.cuda.synchronize()
+            if ref is None:
+                ref, same = outs, True
+            else:
+                cnt = ref[3].reshape(-1).tolist()
+                same = bool(torch.equal(ref[3], outs[3])) and all(
+                    torch.equal(ref[j].reshape(len(cnt), B.PRE_NMS, -1)[s, :c], outs[j].reshape(len(cnt), B.PRE_NMS, -1)[s, :c])
+                    for j in range(3) for s, c in enumerate(cnt))
+            med, mn = timed(fn, args.reps, flush)
+            emit(kernel="rpn_select", variant=name, ms=med, ms_min=mn, GBps=bytes_sel / 1e9 / (med * 1e-3),
+                 frac=bytes_sel / 1e9 / (med * 1e-3) / peak, identical_to_first=same)
+        setenv({})
 
     if "nms" in only:
         boxes, scores, _, counts = ops.rpn_select([obj_d], k=B.PRE_NMS, img_size=(B.IMG_H, B.IMG_W), score_thresh=0.3, min_size=10.0,

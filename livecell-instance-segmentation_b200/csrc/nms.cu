@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, in
 // 3. resolve.  grid S, one CTA of kResolveThreads per segment.
 // Warp 0 owns the serial part (greedy pass over the chunk's 32x32 diagonal block: the 32 diagonal
 // words are broadcast with shuffles up front, the dependent chain is two LOP3 per box); all warps
-// then OR the rows of the kept boxes into the `removed` bit-vector, one word per thread, every
-// thread's loads independent (one L2 round trip per chunk instead of one per kept row).
+// then OR the rows of the kept boxes into the `removed` bit-vector (lane = row, warp = word slot,
+// independent loads + redux.sync: one L2 round trip per chunk instead of one per kept row).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxWords = LCR_MAX_NMS_BOXES / 32;
 constexpr int kResolveThreads = 256;
@@ -257,16 +257,23 @@ __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int stride
     const uint32_t kept = s_kept;
     count += __popc(kept);
     if (count < post_n) {  // block-uniform
-      for (int w = c + 1 + tid; w < nchunks; w += kResolveThreads) {
-        // all 32 row words are loaded unconditionally (independent loads: one L2 round trip, not one per
-        // kept row) and selected afterwards; rows past n are clamped (their kept bit is 0)
-        uint32_t v[32];
+      // lane = row of the chunk, warp = word slot: every thread issues at most four independent loads
+      // (one L2 round trip per chunk), rows are OR-reduced across the warp with redux.sync
+      const bool row_kept = (kept >> lane) & 1u;                       // implies row0 + lane < n
+      const uint32_t* mrow = mask + (size_t)(row0 + lane) * nw;
+      for (int w0 = c + 1 + warp; w0 < nchunks; w0 += 4 * (kResolveThreads / 32)) {
+        uint32_t v[4];
 #pragma unroll
-        for (int b = 0; b < 32; ++b) v[b] = __ldcg(mask + (size_t)min(row0 + b, n - 1) * nw + w);
-        uint32_t acc = 0u;
+        for (int j = 0; j < 4; ++j) {
+          const int w = w0 + j * (kResolveThreads / 32);
+          v[j] = (row_kept && w < nchunks) ? __ldg(mrow + w) : 0u;
+        }
 #pragma unroll
-        for (int b = 0; b < 32; ++b) acc |= ((kept >> b) & 1u) ? v[b] : 0u;
-        removed[w] |= acc;
+        for (int j = 0; j < 4; ++j) {
+          const int w = w0 + j * (kResolveThreads / 32);
+          const uint32_t acc = __reduce_or_sync(0xFFFFFFFFu, v[j]);
+          if (lane == 0 && w < nchunks) removed[w] |= acc;
+        }
       }
     }
     __syncthreads();

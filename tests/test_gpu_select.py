@@ -182,14 +182,31 @@ def test_threshold_first_path_boundaries(ops, oracle):
         hot = rng.choice(flat.size, n_pass, replace=False)
         flat[hot] = rng.permutation(np.linspace(1.0, 9.0, n_pass)).astype(np.float32)    # distinct scores
         check_against_oracle(ops, oracle, obj, 2000, 0.3, 0.0, 160, 192, base)
-    # logits within +-1e-5 of logit(0.3) = -0.8472979: sigmoid lands on both sides of 0.3f
+    # logits within +-2e-5 of logit(0.3) = -0.8472979: sigmoid lands on both sides of 0.3f.  glibc and CUDA expf
+    # differ by ulps there, so this case pins the two GPU paths against EACH OTHER (bit-identical outputs) and
+    # the oracle only on the count being within the handful of borderline elements.
+    import os
     obj = np.full((1, 9, 20, 24), -7.0, np.float32)
     flat = obj.reshape(-1)
     centre = np.float32(np.log(0.3 / 0.7))
     near = centre + (np.arange(-200, 200).astype(np.float32) * np.float32(1e-7))
     flat[rng.choice(flat.size, near.size, replace=False)] = near
     for strict in (True, False):
-        check_against_oracle(ops, oracle, obj, 300, 0.3, 0.0, 80, 96, base, strict=strict)
+        kw = dict(k=300, img_size=(80, 96), score_thresh=0.3, min_size=0.0, strides=[4], base=torch.from_numpy(base),
+                  score_strict=strict)
+        fast = run_select(ops, obj, **kw)
+        os.environ["LCR_SELECT"] = "general"
+        try:
+            general = run_select(ops, obj, **kw)
+        finally:
+            os.environ.pop("LCR_SELECT", None)
+        n = int(fast[3][0, 0])
+        assert n == int(general[3][0, 0]) and 150 < n < 250
+        for a, b in zip(fast[:3], general[:3]):
+            assert np.array_equal(a[0, 0, :n], b[0, 0, :n])
+        _, _, oi = oracle.rpn_select(obj[0], base=base, stride=4, k=300, score_thresh=0.3, score_strict=strict, min_size=0.0,
+                                     img_h=80, img_w=96)
+        assert abs(n - len(oi)) <= 8
     # fewer survivors than k: everything that passes comes out, sorted
     obj = rng.normal(-5, 0.3, size=(2, 9, 20, 24)).astype(np.float32)
     obj.reshape(2, -1)[:, rng.choice(9 * 20 * 24, 37, replace=False)] = rng.uniform(0, 6, size=37).astype(np.float32)

@@ -296,19 +296,41 @@ def run_ours(args):
                 "peak_source": peak_src, "bytes_per_launch": paste_bytes, "ms_per_launch": paste_ms,
                 "share_of_step": stage_ms[3] / max(sum(stage_ms), 1e-9)}
 
-    # NMS latency (BASELINE metric "NMS us"): one 2000-box segment, sorted input, CUDA events
+    # NMS latency (BASELINE metric "NMS us"): one 2000-box segment, sorted input.  The three launches (rank,
+    # mask, resolve) are captured once into a CUDA graph and replayed, so the figure is device time, not the
+    # Python launch path; `nms_us_2000_boxes_eager` is the same call issued eagerly from Python.
     cand_boxes, _, _, cand_counts = ops.rpn_select([obj_d[:1]], k=PRE_NMS, img_size=(IMG_H, IMG_W), score_thresh=0.3, min_size=10.0,
                                                    strides=[4], base=pipe.base)
-    ne = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    for _ in range(5):
-        ops.nms_batched(cand_boxes[:, 0], None, 0.4, post_n=POST_NMS, counts=cand_counts[:, 0].contiguous())
+    nb, nc = cand_boxes[:, 0].contiguous(), cand_counts[:, 0].contiguous()
     reps = 50
+    ne = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for _ in range(5):
+        ops.nms_batched(nb, None, 0.4, post_n=POST_NMS, counts=nc)
     ne[0].record(stream)
     for _ in range(reps):
-        ops.nms_batched(cand_boxes[:, 0], None, 0.4, post_n=POST_NMS, counts=cand_counts[:, 0].contiguous())
+        ops.nms_batched(nb, None, 0.4, post_n=POST_NMS, counts=nc)
     ne[1].record(stream)
     torch.cuda.synchronize()
-    nms_us = ne[0].elapsed_time(ne[1]) * 1e3 / reps
+    nms_us_eager = ne[0].elapsed_time(ne[1]) * 1e3 / reps
+    side = torch.cuda.Stream()
+    side.wait_stream(stream)
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            ops.nms_batched(nb, None, 0.4, post_n=POST_NMS, counts=nc)
+    stream.wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ops.nms_batched(nb, None, 0.4, post_n=POST_NMS, counts=nc)
+    for _ in range(5):
+        graph.replay()
+    ne[2].record(stream)
+    for _ in range(reps):
+        graph.replay()
+    ne[3].record(stream)
+    torch.cuda.synchronize()
+    nms_us = ne[2].elapsed_time(ne[3]) * 1e3 / reps
+    del graph
 
     # ---- e2e: the public host-fed entry point (pipeline.HostFedRegionPipeline.run): every step copies that
     # step's inputs from pinned host memory (chunked, overlapped with compute) and reads the records back ----------
@@ -350,7 +372,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms, "api": f"pipeline.HostFedRegionPipeline.run (chunks of {runner.FC} frames, H2D overlapped with compute)",
                     "d2h": "detection records + counts (pasted masks stay sharded in HBM, SURVEY §8e)",
                     "counts_match_resident_run": e2e_ok},
-            "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "nms_us_2000_boxes": nms_us,
+            "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "nms_us_2000_boxes": nms_us, "nms_us_2000_boxes_eager": nms_us_eager,
             "proposals_per_frame": n_props / F, "detections_per_frame": n_det / F,
         }
         if world == 1 and not args.no_cpu_baseline:

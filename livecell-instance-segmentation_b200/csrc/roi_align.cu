@@ -368,28 +368,34 @@ __global__ void __launch_bounds__(NT, 4) roi_fwd_nhwc_kernel(const __grid_consta
   if (tid == 0) bulk_wait_all();
 }
 
-// ---- forward, warp items (P = 7) -----------------------------------------------------------------
-// A work item is (RoI, 64-channel group) and belongs to ONE warp: lane = channel pair, no block
-// barrier anywhere, every warp streams its own items (table build -> row walk -> 12.5 KB tile ->
-// one bulk store), so the SM always has 16 independent load streams in flight.
+// ---- forward, warp items (P = 7 and P = 14) ------------------------------------------------------
+// A work item belongs to ONE warp: no block barrier anywhere, every warp streams its own items
+// (table build -> row walk -> tile in shared memory -> one bulk store), so the SM always has 16
+// independent load streams in flight.
+//   P = 7 : item = (RoI, 64 channels), lane = channel pair, each lane pools all 7 x-bins.
+//   P = 14: item = (RoI, 32 channels); the two half-warps take x-bins 0-6 and 7-13 of the same 16
+//           channel pairs, so a lane still owns 7 bins (same register budget) and a warp load still
+//           covers whole 128-byte lines (16 lanes x 8 B per column).
 //
 // x direction, "bin-dense": the two samples of a bin touch a contiguous run of <= NB columns
-// (NB = 3 for RoIs up to 14 feature px wide, 4 up to 28).  The per-sample (lo, hi, w_lo, w_hi) taps
-// are folded once per RoI into NB weights per bin, and a window row is pooled with a fixed,
-// branch-free sequence of 7*NB vector loads + 7*NB packed FMAs (no reuse bookkeeping per sample;
-// columns shared by neighbouring bins hit L1).  Wider RoIs take the per-sample path (NB = 0).
+// (NB = 3 for RoIs up to 14 feature px wide at P = 7, 4 up to 28).  The per-sample (lo, hi, w_lo,
+// w_hi) taps are folded once per RoI into NB weights per bin, and a window row is pooled with a
+// fixed, branch-free sequence of 7*NB vector loads + 7*NB packed FMAs (no reuse bookkeeping per
+// sample; columns shared by neighbouring bins hit L1).  Wider RoIs take the per-sample path (NB = 0).
 // y direction: the distinct rows are walked once with the two-row cache (SAME / SHIFT / NEW).
 struct __align__(16) AxisTapB {
   uint32_t off_lo, off_hi;  // BYTE offsets (already multiplied by the axis stride)
   float w_lo, w_hi;
 };
 
+constexpr int kXB = 7;  // x-bins per lane
+
 template <int P>
 struct __align__(16) WarpTables {
   AxisTapB ys[2 * P];
   AxisTapB xs[2 * P];
   float4 xw[P];          // folded weights of the bin's columns xoff, xoff + sw, ... (<= 4 columns)
-  uint32_t xoff[P + 1];  // byte offset of the bin's first column
+  uint32_t xoff[P + 2];  // byte offset of the bin's first column
   uint32_t ymode[2 * P];
   int lo[2][2 * P];      // scratch: neighbour indices per axis (lo = -1: sample contributes nothing)
   int hi[2][2 * P];
@@ -399,6 +405,7 @@ struct __align__(16) WarpTables {
 // path with NB = max(3, run); > 4 -> per-sample path).  All 32 lanes must call.
 template <int P>
 __device__ __forceinline__ int build_tables_warp(WarpTables<P>& tb, const RoiGeom& g, const LvParam& lv, int lane) {
+  static_assert(2 * P <= 32 && P < 31, "one lane per sample");
   __syncwarp();  // the previous item's readers are done with the tables
   if (lane < 2 * P) {
     int lo, hi;
@@ -459,22 +466,23 @@ __device__ __forceinline__ int build_tables_warp(WarpTables<P>& tb, const RoiGeo
 
 __device__ __forceinline__ float2 ldg_f2b(const char* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
-// One window row -> T[pw], x-pooled.  CSW: compile-time column stride in elements (0 = use sw).
+// One window row -> T[0..6] = this lane's 7 x-bins (bins xb0 .. xb0+6), x-pooled.
+// CSW: compile-time column stride in elements (0 = use swb).
 template <int P, int NB, int CSW>
-__device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, const uint32_t (&xo)[P], const char* __restrict__ row,
-                                              uint32_t swb, float2 (&T)[P]) {
+__device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, int xb0, const uint32_t (&xo)[kXB],
+                                              const char* __restrict__ row, uint32_t swb, float2 (&T)[kXB]) {
   const uint32_t cs = CSW ? (uint32_t)CSW * 4u : swb;
   if (NB > 0) {
-    float2 v[P][NB > 0 ? NB : 1];
+    float2 v[kXB][NB > 0 ? NB : 1];
 #pragma unroll
-    for (int pw = 0; pw < P; ++pw) {
+    for (int pw = 0; pw < kXB; ++pw) {
       const char* p = row + xo[pw];
 #pragma unroll
       for (int j = 0; j < NB; ++j) v[pw][j] = ldg_f2b(p + j * cs);
     }
 #pragma unroll
-    for (int pw = 0; pw < P; ++pw) {
-      const float4 w = tb.xw[pw];
+    for (int pw = 0; pw < kXB; ++pw) {
+      const float4 w = tb.xw[xb0 + pw];
       float2 t = __fmul2_rn(splat(w.x), v[pw][0]);
       t = ffma2(splat(w.y), v[pw][1], t);
       if (NB > 2) t = ffma2(splat(w.z), v[pw][2], t);
@@ -482,19 +490,19 @@ __device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, const uin
       T[pw] = t;
     }
   } else {
-    float2 a[2 * P], b[2 * P];
+    float2 a[2 * kXB], b[2 * kXB];
 #pragma unroll
-    for (int t = 0; t < 2 * P; ++t) {
-      const AxisTapB s = tb.xs[t];  // samples that contribute nothing have offsets 0 and weights 0
+    for (int t = 0; t < 2 * kXB; ++t) {
+      const AxisTapB s = tb.xs[2 * xb0 + t];  // samples that contribute nothing have offsets 0 and weights 0
       a[t] = ldg_f2b(row + s.off_lo);
       b[t] = ldg_f2b(row + s.off_hi);
     }
 #pragma unroll
-    for (int pw = 0; pw < P; ++pw) T[pw] = make_float2(0.f, 0.f);
+    for (int pw = 0; pw < kXB; ++pw) T[pw] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int t = 0; t < 2 * P; ++t) {
-      const AxisTapB s = tb.xs[t];
-      if (__any_sync(0xffffffffu, s.w_lo + s.w_hi != 0.f)) {  // warp-uniform
+    for (int t = 0; t < 2 * kXB; ++t) {
+      const AxisTapB s = tb.xs[2 * xb0 + t];
+      if (s.w_lo + s.w_hi != 0.f) {  // uniform per half-warp
         T[t >> 1] = ffma2(splat(s.w_lo), a[t], T[t >> 1]);
         T[t >> 1] = ffma2(splat(s.w_hi), b[t], T[t >> 1]);
       }
@@ -502,24 +510,24 @@ __device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, const uin
   }
 }
 
-// Walks the distinct rows of the window and writes this lane's two channels of the tile.
+// Walks the distinct rows of the window and writes this lane's two channels x 7 x-bins of the tile.
 // Every branch is warp-uniform and says so through a vote, so that ptxas keeps the uniform datapath.
 template <int P, int NB, int CSW>
-__device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, const char* __restrict__ fb, uint32_t swb,
+__device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, int xb0, const char* __restrict__ fb, uint32_t swb,
                                               float* __restrict__ my) {
   constexpr int PP = P * P;
   constexpr uint32_t kAll = 0xffffffffu;
-  float2 T0[P], T1[P], acc[P];
-  uint32_t xo[P];  // bin column offsets stay in registers for the whole RoI
+  float2 T0[kXB], T1[kXB], acc[kXB];
+  uint32_t xo[kXB];  // bin column offsets stay in registers for the whole RoI
 #pragma unroll
-  for (int pw = 0; pw < P; ++pw) {
+  for (int pw = 0; pw < kXB; ++pw) {
     T0[pw] = T1[pw] = acc[pw] = make_float2(0.f, 0.f);
-    xo[pw] = NB > 0 ? tb.xoff[pw] : 0u;
+    xo[pw] = NB > 0 ? tb.xoff[xb0 + pw] : 0u;
   }
-  // Tile stores without bank conflicts: the lane's channel rows start 98 words apart, so lanes l and l+16
-  // share banks; the upper half-warp therefore stores its odd channel while the lower stores its even one
-  // (49 words = 17 banks apart) and vice versa.
-  const bool lower = (threadIdx.x & 16) == 0;
+  // P = 7, tile stores without bank conflicts: the lane's channel rows start 98 words apart, so lanes l and
+  // l+16 share banks; the upper half-warp therefore stores its odd channel while the lower stores its even
+  // one (49 words = 17 banks apart) and vice versa.  (P = 14: plain order.)
+  const bool lower = P != 7 || (threadIdx.x & 16) == 0;
   float* const o_a = my + (lower ? 0 : PP);
   float* const o_b = my + (lower ? PP : 0);
 #pragma unroll 1
@@ -530,20 +538,20 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, const cha
       const AxisTapB s = tb.ys[t];
       if (__any_sync(kAll, mode == kShift)) {
 #pragma unroll
-        for (int pw = 0; pw < P; ++pw) T0[pw] = T1[pw];
+        for (int pw = 0; pw < kXB; ++pw) T0[pw] = T1[pw];
       } else if (__any_sync(kAll, mode == kNew)) {
-        pool_row_warp<P, NB, CSW>(tb, xo, fb + s.off_lo, swb, T0);
+        pool_row_warp<P, NB, CSW>(tb, xb0, xo, fb + s.off_lo, swb, T0);
       }
       if (__any_sync(kAll, mode != kSame)) {
         if (__any_sync(kAll, m & kBorder)) {
 #pragma unroll
-          for (int pw = 0; pw < P; ++pw) T1[pw] = T0[pw];
+          for (int pw = 0; pw < kXB; ++pw) T1[pw] = T0[pw];
         } else {
-          pool_row_warp<P, NB, CSW>(tb, xo, fb + s.off_hi, swb, T1);
+          pool_row_warp<P, NB, CSW>(tb, xb0, xo, fb + s.off_hi, swb, T1);
         }
       }
 #pragma unroll
-      for (int pw = 0; pw < P; ++pw) {
+      for (int pw = 0; pw < kXB; ++pw) {
         acc[pw] = ffma2(splat(s.w_lo), T0[pw], acc[pw]);
         acc[pw] = ffma2(splat(s.w_hi), T1[pw], acc[pw]);
       }
@@ -551,7 +559,7 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, const cha
     if (t & 1) {  // bin row complete; count = 4 for sampling_ratio 2: multiply by 0.25 is exact
       const int o = (t >> 1) * P;
 #pragma unroll
-      for (int pw = 0; pw < P; ++pw) {
+      for (int pw = 0; pw < kXB; ++pw) {
         const float e = acc[pw].x * 0.25f, f = acc[pw].y * 0.25f;
         o_a[o + pw] = lower ? e : f;
         o_b[o + pw] = lower ? f : e;
@@ -572,20 +580,29 @@ __device__ __forceinline__ void bulk_store_smem_to_global_hint(void* gdst, const
                : "memory");
 }
 
-constexpr int kWarpChannels = 64;  // channels per warp item (lane = channel pair)
+template <int P>
+struct WarpItem {
+  static constexpr int kHalves = P / kXB;                 // 1 (P = 7) or 2 (P = 14): x-bin groups per warp
+  static constexpr int kPairs = 32 / kHalves;             // channel pairs per warp item
+  static constexpr int kChannels = 2 * kPairs;            // 64 or 32
+  static constexpr int kTileFloats = kChannels * P * P;   // 12 544 B or 25 088 B
+};
 
 template <int P, int WARPS, int CSW>
-__global__ void __launch_bounds__(WARPS * 32, 4) roi_fwd_warp_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out,
-                                                                    int groups, int stream_out, int ipw) {
+__global__ void __launch_bounds__(WARPS * 32, P == 7 ? 4 : 2)
+    roi_fwd_warp_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out, int groups, int stream_out, int ipw) {
+  using WI = WarpItem<P>;
+  static_assert(P % kXB == 0 && WI::kHalves <= 2, "P must be 7 or 14");
   constexpr int PP = P * P;
-  constexpr int TILE = kWarpChannels * PP;  // floats
   constexpr uint32_t kAll = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = __shfl_sync(kAll, (int)(threadIdx.x >> 5), 0);  // tells ptxas the value is warp-uniform
   const int lane = threadIdx.x & 31;
-  float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * TILE;
-  WarpTables<P>& tb = reinterpret_cast<WarpTables<P>*>(smem_raw + sizeof(float) * WARPS * TILE)[warp];
-  float* my = tile + (size_t)(2 * lane) * PP;
+  const int pair = lane % WI::kPairs;          // channel pair of this lane inside the item
+  const int xb0 = (lane / WI::kPairs) * kXB;   // first x-bin of this lane
+  float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * WI::kTileFloats;
+  WarpTables<P>& tb = reinterpret_cast<WarpTables<P>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats)[warp];
+  float* my = tile + (size_t)(2 * pair) * PP + xb0;
   const uint64_t pol = l2_policy_evict_first();
   const long long items = (long long)p.K * groups;
   // Work order.  ipw > 0: CTA b owns the WARPS*ipw consecutive items starting at b*WARPS*ipw (warp w takes
@@ -600,8 +617,8 @@ __global__ void __launch_bounds__(WARPS * 32, 4) roi_fwd_warp_kernel(const __gri
   for (long long item = first; item < last; item += stride) {
     const int k = (int)(item / groups);
     const int cg = (int)(item - (long long)k * groups);
-    const int c0 = cg * kWarpChannels;
-    const int nch = min(kWarpChannels, p.C - c0);  // multiple of 4
+    const int c0 = cg * WI::kChannels;
+    const int nch = min(WI::kChannels, p.C - c0);  // multiple of 4
     const RoiGeom g = roi_geom(p, k);
     const bool live = __any_sync(kAll, g.live);
     const LvParam& lv = p.lv[live ? g.lvl : 0];
@@ -611,15 +628,14 @@ __global__ void __launch_bounds__(WARPS * 32, 4) roi_fwd_warp_kernel(const __gri
     if (lane == 0) bulk_wait_read_all();
     __syncwarp();
     if (!live) {
-#pragma unroll 7
-      for (int j = 0; j < 2 * PP; ++j) my[j] = 0.f;
+      for (int j = lane; j < WI::kTileFloats; j += 32) tile[j] = 0.f;
     } else {
       // lanes past the last channel pair of a short group redo the last pair (their tile rows are not stored)
-      const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)g.b * lv.sn + c0 + min(2 * lane, nch - 2));  // sc == 1
+      const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)g.b * lv.sn + c0 + min(2 * pair, nch - 2));  // sc == 1
       const uint32_t swb = (uint32_t)lv.sw * 4u;
-      if (__all_sync(kAll, run <= 3)) roi_warp_body<P, 3, CSW>(tb, fb, swb, my);
-      else if (__all_sync(kAll, run == 4)) roi_warp_body<P, 4, CSW>(tb, fb, swb, my);
-      else roi_warp_body<P, 0, CSW>(tb, fb, swb, my);
+      if (__all_sync(kAll, run <= 3)) roi_warp_body<P, 3, CSW>(tb, xb0, fb, swb, my);
+      else if (__all_sync(kAll, run == 4)) roi_warp_body<P, 4, CSW>(tb, xb0, fb, swb, my);
+      else roi_warp_body<P, 0, CSW>(tb, xb0, fb, swb, my);
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -700,7 +716,7 @@ __device__ __forceinline__ void scatter_row(const RoiTables<P>& tb, float* __res
 
 template <int P, int NT>
 __global__ void __launch_bounds__(NT, 4) roi_bwd_nhwc_kernel(const __grid_constant__ RoiParams p, const float* __restrict__ gout,
-                                                          int groups) {
+                                                          int groups, int ipc) {
   constexpr int CPB = 2 * NT;
   constexpr int PP = P * P;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -716,7 +732,10 @@ __global__ void __launch_bounds__(NT, 4) roi_bwd_nhwc_kernel(const __grid_consta
   __syncthreads();
   uint32_t parity = 0;
 
-  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+  // CTA b owns the ipc consecutive items starting at b*ipc: CTAs launch in index order, so the RoIs in flight
+  // are neighbours in the list and the gradient lines they hit stay L2-resident (see roi_fwd_warp_kernel)
+  const long long last = min(items, ((long long)blockIdx.x + 1) * ipc);
+  for (long long item = (long long)blockIdx.x * ipc; item < last; ++item) {
     const int k = (int)(item / groups);
     const int cg = (int)(item - (long long)k * groups);
     const int c0 = cg * CPB;
@@ -848,7 +867,10 @@ static int launch_fast(const RoiParams& p, float* out_or_gout, cudaStream_t st) 
       if (e != cudaSuccess) return cuda_status(e);
       configured_dev = dev;
     }
-    kern<<<blocks, NT, smem, st>>>(p, out_or_gout, groups);
+    const int ipc = 2;
+    const long long nb = (items + ipc - 1) / ipc;
+    LCR_REQUIRE(nb < (1ll << 31), LCR_ERR_CAPACITY);
+    kern<<<(unsigned)nb, NT, smem, st>>>(p, out_or_gout, groups, ipc);
   } else {
     auto kern = roi_fwd_nhwc_kernel<P, NT>;
     if (configured_dev != dev) {
@@ -870,9 +892,10 @@ static bool env_is(const char* name, const char* value) {
 
 template <int P, int CSW>
 static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
+  using WI = WarpItem<P>;
   constexpr int WARPS = 4;
-  const int groups = (p.C + kWarpChannels - 1) / kWarpChannels;
-  const size_t smem = sizeof(float) * WARPS * kWarpChannels * P * P + WARPS * sizeof(WarpTables<P>);
+  const int groups = (p.C + WI::kChannels - 1) / WI::kChannels;
+  const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<P>);
   const long long items = (long long)p.K * groups;
   int ipw = 2;  // items per warp per CTA
   if (const char* v = getenv("LCR_ROI_IPW")) ipw = atoi(v);
@@ -901,7 +924,6 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
 
 // warp-item kernel: additionally every map at least 4 columns wide
 static bool warp_eligible(const RoiParams& p) {
-  if (p.PH != 7) return false;
   for (int l = 0; l < p.L; ++l)
     if (p.lv[l].W < 4) return false;
   return true;
@@ -927,8 +949,8 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
   cudaStream_t st = as_stream(stream);
   if (fast_eligible(p, out)) {
     if (warp_eligible(p) && !env_is("LCR_ROI_FWD", "cta")) {
-      if (all_sw_equal(p, 256)) return launch_fwd_warp<7, 256>(p, out, st);
-      return launch_fwd_warp<7, 0>(p, out, st);
+      if (PH == 7) return all_sw_equal(p, 256) ? launch_fwd_warp<7, 256>(p, out, st) : launch_fwd_warp<7, 0>(p, out, st);
+      return all_sw_equal(p, 256) ? launch_fwd_warp<14, 256>(p, out, st) : launch_fwd_warp<14, 0>(p, out, st);
     }
     if (PH == 7) return launch_fast<7, 128, false>(p, out, st);
     return launch_fast<14, 32, false>(p, out, st);

@@ -396,6 +396,7 @@ struct __align__(16) WarpTables {
   AxisTapB xs[2 * P];
   float4 xw[P];          // folded weights of the bin's columns xoff, xoff + sw, ... (<= 4 columns)
   uint32_t xoff[P + 2];  // byte offset of the bin's first column
+  int xfirst[P + 2];     // its column index (backward: how far the accumulator window slides between bins)
   uint32_t ymode[2 * P];
   int lo[2][2 * P];      // scratch: neighbour indices per axis (lo = -1: sample contributes nothing)
   int hi[2][2 * P];
@@ -458,6 +459,7 @@ __device__ __forceinline__ int build_tables_warp(WarpTables<P>& tb, const RoiGeo
       }
     }
     tb.xoff[lane] = (uint32_t)(first * lv.sw) * 4u;
+    tb.xfirst[lane] = first;
   }
   run = __reduce_max_sync(0xffffffffu, run);
   __syncwarp();
@@ -813,6 +815,183 @@ __global__ void __launch_bounds__(NT, 4) roi_bwd_nhwc_kernel(const __grid_consta
   }
 }
 
+// ---- backward, warp items (P = 7 and P = 14) ------------------------------------------------------
+// The transpose of roi_fwd_warp_kernel (same item shapes): the warp's grad_out tile (12.5 / 25 KB) arrives
+// with one bulk load on the warp's own mbarrier; the y direction accumulates, per distinct window row,
+// U[pw] = sum of w * grad_out[ph][pw] / 4 with the same two-row cache; a row that leaves the cache is
+// scattered ONCE: the folded bin weights are walked with a sliding window of NB column accumulators,
+// so every distinct column of the row receives exactly one vector red.global.add (lanes = consecutive
+// channel pairs: a warp's reduction covers two full 128-byte lines at L2).
+// One call site for the row scatter (the r01 kernel inlined it five times and was bound by instruction
+// cache misses: no_instruction stall 10 per issue, ncu r01b).
+__device__ __forceinline__ void red_add_f2(char* p, float2 v, bool active) {
+  if (active) atomicAdd(reinterpret_cast<float2*>(p), v);
+}
+
+template <int P, int NB, int CSW>
+__device__ __forceinline__ void scatter_row_warp(const WarpTables<P>& tb, int xb0, const uint32_t (&xo)[kXB], const int (&xstep)[kXB],
+                                                 char* __restrict__ row, uint32_t swb, const float2 (&U)[kXB], bool active) {
+  const uint32_t cs = CSW ? (uint32_t)CSW * 4u : swb;
+  if (NB > 0) {
+    float2 A[NB > 0 ? NB : 1];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) A[j] = make_float2(0.f, 0.f);
+    uint32_t base = xo[0];
+#pragma unroll
+    for (int pw = 0; pw < kXB; ++pw) {
+      if (pw > 0) {
+        const int d = min(xstep[pw], NB);  // columns the window slides (uniform per half-warp)
+#pragma unroll 1
+        for (int q = 0; q < d; ++q) {
+          red_add_f2(row + base + q * cs, A[0], active);
+#pragma unroll
+          for (int j = 0; j + 1 < NB; ++j) A[j] = A[j + 1];
+          A[NB - 1] = make_float2(0.f, 0.f);
+        }
+        base = xo[pw];
+      }
+      const float4 w = tb.xw[xb0 + pw];
+      A[0] = ffma2(splat(w.x), U[pw], A[0]);
+      A[1] = ffma2(splat(w.y), U[pw], A[1]);
+      if (NB > 2) A[2] = ffma2(splat(w.z), U[pw], A[2]);
+      if (NB > 3) A[3] = ffma2(splat(w.w), U[pw], A[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) red_add_f2(row + base + j * cs, A[j], active);
+  } else {
+#pragma unroll
+    for (int t = 0; t < 2 * kXB; ++t) {
+      const AxisTapB s = tb.xs[2 * xb0 + t];
+      if (s.w_lo + s.w_hi != 0.f) {  // uniform per half-warp
+        red_add_f2(row + s.off_lo, make_float2(s.w_lo * U[t >> 1].x, s.w_lo * U[t >> 1].y), active);
+        red_add_f2(row + s.off_hi, make_float2(s.w_hi * U[t >> 1].x, s.w_hi * U[t >> 1].y), active);
+      }
+    }
+  }
+}
+
+template <int P, int NB, int CSW>
+__device__ __forceinline__ void roi_warp_body_bwd(const WarpTables<P>& tb, int xb0, char* __restrict__ fb, uint32_t swb,
+                                                  const float* __restrict__ my, bool active) {
+  constexpr int PP = P * P;
+  constexpr uint32_t kAll = 0xffffffffu;
+  float2 U0[kXB], U1[kXB], gq[kXB];
+  uint32_t xo[kXB];
+  int xstep[kXB];
+#pragma unroll
+  for (int pw = 0; pw < kXB; ++pw) {
+    U0[pw] = U1[pw] = gq[pw] = make_float2(0.f, 0.f);
+    xo[pw] = NB > 0 ? tb.xoff[xb0 + pw] : 0u;
+    xstep[pw] = (NB > 0 && pw > 0) ? tb.xfirst[xb0 + pw] - tb.xfirst[xb0 + pw - 1] : 0;
+  }
+  // P = 7: conflict-free tile reads, see the forward kernel's store order
+  const bool lower = P != 7 || (threadIdx.x & 16) == 0;
+  const float* const i_a = my + (lower ? 0 : PP);
+  const float* const i_b = my + (lower ? PP : 0);
+  uint32_t r0 = 0xffffffffu, r1 = 0xffffffffu;  // byte offsets of the two cached rows (all-ones: empty)
+#pragma unroll 1
+  for (int t = 0; t <= 2 * P; ++t) {  // the extra iteration flushes both rows
+    const uint32_t m = t < 2 * P ? tb.ymode[t] : (kValid | kNew);
+    if (!(t & 1) && t < 2 * P) {  // entering bin row t/2: grad_out[ph][:] / count (count = 4, exact)
+      const int o = (t >> 1) * P;
+#pragma unroll
+      for (int pw = 0; pw < kXB; ++pw) {
+        const float e = i_a[o + pw] * 0.25f, f = i_b[o + pw] * 0.25f;
+        gq[pw] = lower ? make_float2(e, f) : make_float2(f, e);
+      }
+    }
+    if (__any_sync(kAll, m & kValid)) {
+      const uint32_t mode = m & kModeMask;
+      const int nflush = __any_sync(kAll, mode == kShift) ? 1 : (__any_sync(kAll, mode == kNew) ? 2 : 0);
+#pragma unroll 1
+      for (int f = 0; f < nflush; ++f) {  // the single scatter site
+        if (__any_sync(kAll, r0 != 0xffffffffu)) scatter_row_warp<P, NB, CSW>(tb, xb0, xo, xstep, fb + r0, swb, U0, active);
+#pragma unroll
+        for (int pw = 0; pw < kXB; ++pw) {
+          U0[pw] = U1[pw];
+          U1[pw] = make_float2(0.f, 0.f);
+        }
+        r0 = r1;
+        r1 = 0xffffffffu;
+      }
+      if (t < 2 * P) {
+        const AxisTapB s = tb.ys[t];
+        r0 = s.off_lo;
+        if (__any_sync(kAll, m & kBorder)) {
+#pragma unroll
+          for (int pw = 0; pw < kXB; ++pw) {
+            U0[pw] = ffma2(splat(s.w_lo), gq[pw], U0[pw]);
+            U0[pw] = ffma2(splat(s.w_hi), gq[pw], U0[pw]);
+          }
+        } else {
+          r1 = s.off_hi;
+#pragma unroll
+          for (int pw = 0; pw < kXB; ++pw) {
+            U0[pw] = ffma2(splat(s.w_lo), gq[pw], U0[pw]);
+            U1[pw] = ffma2(splat(s.w_hi), gq[pw], U1[pw]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int P, int WARPS, int CSW>
+__global__ void __launch_bounds__(WARPS * 32, P == 7 ? 4 : 2)
+    roi_bwd_warp_kernel(const __grid_constant__ RoiParams p, const float* __restrict__ gout, int groups, int ipw) {
+  using WI = WarpItem<P>;
+  constexpr int PP = P * P;
+  constexpr uint32_t kAll = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = __shfl_sync(kAll, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int pair = lane % WI::kPairs;
+  const int xb0 = (lane / WI::kPairs) * kXB;
+  float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * WI::kTileFloats;
+  WarpTables<P>& tb = reinterpret_cast<WarpTables<P>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats)[warp];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<P>)) + warp;
+  const float* my = tile + (size_t)(2 * pair) * PP + xb0;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  const long long items = (long long)p.K * groups;
+  const long long first = (long long)blockIdx.x * WARPS * ipw + warp;
+  const long long last = min(items, ((long long)blockIdx.x + 1) * WARPS * ipw);
+
+  for (long long item = first; item < last; item += WARPS) {
+    const int k = (int)(item / groups);
+    const int cg = (int)(item - (long long)k * groups);
+    const int c0 = cg * WI::kChannels;
+    const int nch = min(WI::kChannels, p.C - c0);
+    const RoiGeom g = roi_geom(p, k);
+    if (!__any_sync(kAll, g.live)) continue;  // warp-uniform
+    const LvParam& lv = p.lv[g.lvl];
+    fence_proxy_async_smem();  // generic-proxy reads of the old tile are ordered before the async-proxy refill
+    __syncwarp();              // every lane is done with the previous tile
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(nch * PP * sizeof(float));
+      mbar_expect_tx(bar, bytes);
+      bulk_load_global_to_smem(tile, gout + ((size_t)k * p.C + c0) * PP, bytes, bar);
+    }
+    const int run = build_tables_warp<P>(tb, g, lv, lane);
+    bool mono = true;  // the sliding window needs non-decreasing bin starts (always true for x2 >= x1)
+    if (lane > 0 && lane < P) mono = tb.xfirst[lane] >= tb.xfirst[lane - 1];
+    mono = __all_sync(kAll, mono);
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    // every lane runs the (vote-synchronised) walk; lanes past a short channel group only skip the atomics
+    const bool active = 2 * pair < nch;
+    char* fb = reinterpret_cast<char*>(lv.data + (size_t)g.b * lv.sn + c0 + min(2 * pair, nch - 2));
+    const uint32_t swb = (uint32_t)lv.sw * 4u;
+    if (mono && run <= 3) roi_warp_body_bwd<P, 3, CSW>(tb, xb0, fb, swb, my, active);
+    else if (mono && run == 4) roi_warp_body_bwd<P, 4, CSW>(tb, xb0, fb, swb, my, active);
+    else roi_warp_body_bwd<P, 0, CSW>(tb, xb0, fb, swb, my, active);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -922,6 +1101,29 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
   return after_launch();
 }
 
+template <int P, int CSW>
+static int launch_bwd_warp(const RoiParams& p, const float* gout, cudaStream_t st) {
+  using WI = WarpItem<P>;
+  constexpr int WARPS = 4;
+  const int groups = (p.C + WI::kChannels - 1) / WI::kChannels;
+  const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<P>) + WARPS * 8;
+  const long long items = (long long)p.K * groups;
+  const int ipw = 2;
+  const long long want = (items + (long long)WARPS * ipw - 1) / ((long long)WARPS * ipw);
+  LCR_REQUIRE(want < (1ll << 31), LCR_ERR_CAPACITY);
+  auto kern = roi_bwd_warp_kernel<P, WARPS, CSW>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    configured_dev = dev;
+  }
+  kern<<<(unsigned)want, WARPS * 32, smem, st>>>(p, gout, groups, ipw);
+  return after_launch();
+}
+
 // warp-item kernel: additionally every map at least 4 columns wide
 static bool warp_eligible(const RoiParams& p) {
   for (int l = 0; l < p.L; ++l)
@@ -980,6 +1182,10 @@ extern "C" int lcr_roi_align_bwd_f32(const float* grad_out, const LcrFeatLevel* 
   if (K == 0) return LCR_OK;
   LCR_REQUIRE(grad_out, LCR_ERR_INVALID_ARG);
   if (fast_eligible(p, grad_out)) {
+    if (warp_eligible(p) && !env_is("LCR_ROI_BWD", "cta")) {
+      if (PH == 7) return all_sw_equal(p, 256) ? launch_bwd_warp<7, 256>(p, grad_out, st) : launch_bwd_warp<7, 0>(p, grad_out, st);
+      return all_sw_equal(p, 256) ? launch_bwd_warp<14, 256>(p, grad_out, st) : launch_bwd_warp<14, 0>(p, grad_out, st);
+    }
     if (PH == 7) return launch_fast<7, 128, true>(p, const_cast<float*>(grad_out), st);
     return launch_fast<14, 32, true>(p, const_cast<float*>(grad_out), st);
   }

@@ -96,9 +96,21 @@ def main():
         gout = torch.randn((F * B.POST_NMS, B.C, 7, 7), generator=g, device=dev)
         gin = torch.empty((F, B.C, B.FH, B.FW), device=dev).contiguous(memory_format=torch.channels_last)
         bytes_bwd = 4 * n_props * B.C * 49 + 3 * F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS
-        med, mn = timed(lambda: ops.roi_align_bwd(gout, [gin], [0.25], props.rois, None, 2, False, zero_grad=True), max(3, args.reps // 2), flush)
-        emit(kernel="roi_align_bwd(+zero fill)", variant="default", ms=med, ms_min=mn, GBps=bytes_bwd / 1e9 / (med * 1e-3),
-             frac=bytes_bwd / 1e9 / (med * 1e-3) / peak)
+        ref = None
+        for name, env in [("cta(r01)", {"LCR_ROI_BWD": "cta"}), ("warp", {})]:
+            setenv(env)
+            ops.roi_align_bwd(gout, [gin], [0.25], props.rois, None, 2, False, zero_grad=True)
+            torch.cuda.synchronize()
+            if ref is None:
+                ref, err = gin.clone(), 0.0
+            else:
+                err = float((gin - ref).abs().max() / ref.abs().max())
+            med, mn = timed(lambda: ops.roi_align_bwd(gout, [gin], [0.25], props.rois, None, 2, False, zero_grad=True),
+                            max(3, args.reps // 2), flush)
+            emit(kernel="roi_align_bwd(+zero fill)", variant=name, ms=med, ms_min=mn, GBps=bytes_bwd / 1e9 / (med * 1e-3),
+                 frac=bytes_bwd / 1e9 / (med * 1e-3) / peak, rel_err_vs_first=err)
+        setenv({})
+        del ref
         del gout, gin
 
     if "paste" in only:

@@ -291,8 +291,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     paste_ms = float(np.mean([pe[2 * i].elapsed_time(pe[2 * i + 1]) for i in range(args.steps)]))
     paste_bytes = n_det * (IMG_H * IMG_W + M * M * 4 + 16)
+    traffic = None     # dram bytes per launch of the same kernel/workload from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("frames_per_gpu") == F and n_det == F * MAX_DET:
+            traffic = tj["paste_bulk_kernel"]["dram_bytes_per_launch"]
     roofline = {"kernel": "paste_bulk_kernel", "bound": "hbm", "achieved": paste_bytes / 1e9 / (paste_ms * 1e-3), "peak": peak,
-                "unit": "GB/s", "frac": paste_bytes / 1e9 / (paste_ms * 1e-3) / peak, "traffic": None,
+                "unit": "GB/s", "frac": paste_bytes / 1e9 / (paste_ms * 1e-3) / peak, "traffic": traffic,
+                "traffic_source": "profiles/ncu_traffic.json (ncu --set full, same workload)" if traffic else None,
                 "peak_source": peak_src, "bytes_per_launch": paste_bytes, "ms_per_launch": paste_ms,
                 "share_of_step": stage_ms[3] / max(sum(stage_ms), 1e-9)}
 

@@ -227,6 +227,28 @@ int lcr_paste_masks_u8(const float* probs, const float* boxes, const uint8_t* va
 int lcr_pack_records_f32(const float* boxes, const float* scores, const int* counts, int S,
                          int stride, float* records, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training-side siblings of the region path.
+ *
+ * Box IoU.  Replaces torchvision.ops.box_iou (TV:ops/boxes.py:308-370) as called at
+ * src/components/rpn.py:72, src/custom_maskrcnn.py:221,249, src/utils/mask_utils.py:93:
+ *   iou[i][j] = inter / ((area_i + area_j) - inter), fp32, no +1, 0/0 = NaN.
+ * lcr_box_iou_f32 writes the [N,G] matrix; lcr_box_iou_max_f32 fuses the `ious.max(dim=1)` that
+ * follows every call site (first index of the maximum; NaN propagates and wins) and never
+ * materialises the matrix.  boxes [N,4], gt [G,4]; max_iou [N] f32, argmax [N] i64.
+ * ---------------------------------------------------------------------------------------------- */
+int lcr_box_iou_f32(const float* boxes, int N, const float* gt, int G, float* iou, void* stream);
+int lcr_box_iou_max_f32(const float* boxes, int N, const float* gt, int G, float* max_iou,
+                        int64_t* argmax, void* stream);
+
+/* Mask targets, batched.  Replaces the per-positive loop over extract_mask_target
+ * (src/utils/mask_utils.py:6-46, :110-113): for target k, crop gt_masks[gt_index[k]] (uint8 [H,W]) to
+ * the int-truncated, clipped box (x1 in [0,W-1], x2 in [x1+1,W], same for y) and resize bilinearly
+ * (align_corners=False) to M x M floats.  gt_index == NULL: target k uses mask k.  An index outside
+ * [0,G) yields an all-zero target.  gt_masks [G,H,W] u8, boxes [K,4] f32, out [K,M,M] f32. */
+int lcr_mask_targets_f32(const uint8_t* gt_masks, int G, int H, int W, const float* boxes,
+                         const int64_t* gt_index, int K, int M, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

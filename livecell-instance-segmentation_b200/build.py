@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 OBJ_DIR = os.path.join(CSRC, "_obj")
 LIB_PATH = os.path.join(CSRC, "liblcr.so")
 
-SOURCES = ["api.cu", "boxes.cu", "layout.cu", "paste.cu", "nms.cu", "roi_align.cu", "rpn_select.cu"]
+SOURCES = ["api.cu", "boxes.cu", "layout.cu", "paste.cu", "nms.cu", "roi_align.cu", "rpn_select.cu", "match.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -1,0 +1,160 @@
+// match.cu — training-side siblings of the region path.
+//
+//   * box IoU matrix and the fused row max / argmax.  Replaces torchvision.ops.box_iou
+//     (TV:ops/boxes.py:308-370: lt/rb broadcast -> [N,G,2] temporaries -> clamp -> inter -> union ->
+//     divide, ~8 ATen launches) and the `ious.max(dim=1)` that follows it at
+//     src/components/rpn.py:72-73, src/custom_maskrcnn.py:221-222,249-250, src/utils/mask_utils.py:93-94.
+//     The fused kernel never materialises the [N,G] matrix: 16 B in + 12 B out per anchor.
+//   * mask-target extraction, batched.  Replaces the per-positive Python loop over
+//     extract_mask_target (src/utils/mask_utils.py:6-46, called at :110-113): int-box crop of the
+//     matched uint8 ground-truth mask + bilinear resize (align_corners=False) to M x M, with two
+//     `.item()` host syncs per proposal in the reference.
+//
+// IoU arithmetic is torchvision's, operation for operation (fp32, no contraction):
+//   area = (x2-x1)*(y2-y1); wh = max(min(rb) - max(lt), 0); inter = w*h; iou = inter/((a1+a2)-inter).
+// Row max follows torch.max(dim=1): first index of the maximum, NaN (0/0: two zero-area boxes)
+// propagates and wins.
+#include "common.cuh"
+
+namespace lcr {
+
+constexpr int kIouThreads = 256;
+constexpr int kGtChunk = 1024;
+
+__device__ __forceinline__ float iou_tv(const float4 a, float area_a, const float4 b, float area_b) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+  const float inter = __fmul_rn(w, h);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  if (inter == 0.f && uni > 0.f) return 0.f;  // the common case: no IEEE division
+  return __fdiv_rn(inter, uni);
+}
+
+__device__ __forceinline__ float box_area_tv(const float4 b) { return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y)); }
+
+// One thread per row box; ground-truth boxes staged through shared memory in chunks.
+template <bool FULL>
+__global__ void __launch_bounds__(kIouThreads) iou_kernel(const float4* __restrict__ boxes, int N, const float4* __restrict__ gt, int G,
+                                                          float* __restrict__ iou_out, float* __restrict__ max_out,
+                                                          long long* __restrict__ arg_out) {
+  __shared__ float4 s_gt[kGtChunk];
+  __shared__ float s_area[kGtChunk];
+  const int i = blockIdx.x * kIouThreads + threadIdx.x;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < N) a = __ldg(boxes + i);
+  const float area_a = box_area_tv(a);
+  float best = 0.f;
+  int best_j = 0;
+  bool best_nan = false, have = false;
+  for (int g0 = 0; g0 < G; g0 += kGtChunk) {
+    const int ng = min(kGtChunk, G - g0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < ng; j += kIouThreads) {
+      const float4 b = __ldg(gt + g0 + j);
+      s_gt[j] = b;
+      s_area[j] = box_area_tv(b);
+    }
+    __syncthreads();
+    if (i < N) {
+      for (int j = 0; j < ng; ++j) {
+        const float v = iou_tv(a, area_a, s_gt[j], s_area[j]);
+        if (FULL) {
+          iou_out[(size_t)i * G + g0 + j] = v;
+        } else if (!best_nan && (!have || v > best || v != v)) {
+          best = v;
+          best_j = g0 + j;
+          best_nan = (v != v);
+          have = true;
+        }
+      }
+    }
+  }
+  if (!FULL && i < N) {
+    max_out[i] = best;
+    arg_out[i] = (long long)best_j;
+  }
+}
+
+// ATen upsample_bilinear2d source index (align_corners=False), see paste.cu / SURVEY App. B.4.
+__device__ __forceinline__ void src_index_mt(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);
+  src = src < 0.f ? 0.f : src;
+  i0 = min(__float2int_rz(src), in_size - 1);
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = __fsub_rn(src, (float)i0);
+  l0 = __fsub_rn(1.0f, l1);
+}
+
+// One CTA per target: M*M outputs, each a bilinear tap of the cropped uint8 mask.
+__global__ void __launch_bounds__(256) mask_targets_kernel(const uint8_t* __restrict__ gt_masks, int G, int H, int W,
+                                                           const float4* __restrict__ boxes, const long long* __restrict__ gt_index,
+                                                           int K, int M, float* __restrict__ out) {
+  const int k = blockIdx.x;
+  const long long gi = gt_index ? gt_index[k] : (long long)k;
+  float* o = out + (size_t)k * M * M;
+  if (gi < 0 || gi >= G) {  // unmatched slot: zeros
+    for (int i = threadIdx.x; i < M * M; i += blockDim.x) o[i] = 0.f;
+    return;
+  }
+  const float4 b = __ldg(boxes + k);
+  // x1, y1, x2, y2 = box.int(); clip exactly as src/utils/mask_utils.py:23-31
+  int x1 = __float2int_rz(b.x), y1 = __float2int_rz(b.y), x2 = __float2int_rz(b.z), y2 = __float2int_rz(b.w);
+  x1 = max(0, min(x1, W - 1));
+  y1 = max(0, min(y1, H - 1));
+  x2 = max(x1 + 1, min(x2, W));
+  y2 = max(y1 + 1, min(y2, H));
+  const int ch = y2 - y1, cw = x2 - x1;
+  const float sh = __fdiv_rn((float)ch, (float)M), sw = __fdiv_rn((float)cw, (float)M);
+  const uint8_t* m = gt_masks + (size_t)gi * H * W + (size_t)y1 * W + x1;
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+    const int oy = i / M, ox = i - oy * M;
+    int h0, h1, w0, w1;
+    float wy0, wy1, wx0, wx1;
+    src_index_mt(sh, oy, ch, h0, h1, wy0, wy1);
+    src_index_mt(sw, ox, cw, w0, w1, wx0, wx1);
+    const float a = (float)m[(size_t)h0 * W + w0], bq = (float)m[(size_t)h0 * W + w1];
+    const float c = (float)m[(size_t)h1 * W + w0], d = (float)m[(size_t)h1 * W + w1];
+    const float top = __fmaf_rn(a, wx0, __fmul_rn(bq, wx1));
+    const float bot = __fmaf_rn(c, wx0, __fmul_rn(d, wx1));
+    o[i] = __fmaf_rn(top, wy0, __fmul_rn(bot, wy1));
+  }
+}
+
+}  // namespace lcr
+
+using namespace lcr;
+
+extern "C" int lcr_box_iou_f32(const float* boxes, int N, const float* gt, int G, float* iou, void* stream) {
+  LCR_REQUIRE(N >= 0 && G >= 0, LCR_ERR_INVALID_ARG);
+  if (N == 0 || G == 0) return LCR_OK;
+  LCR_REQUIRE(boxes && gt && iou, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(aligned_to(boxes, 16) && aligned_to(gt, 16), LCR_ERR_ALIGNMENT);
+  iou_kernel<true><<<(N + kIouThreads - 1) / kIouThreads, kIouThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(boxes), N, reinterpret_cast<const float4*>(gt), G, iou, nullptr, nullptr);
+  return after_launch();
+}
+
+extern "C" int lcr_box_iou_max_f32(const float* boxes, int N, const float* gt, int G, float* max_iou, int64_t* argmax,
+                                   void* stream) {
+  LCR_REQUIRE(N >= 0 && G > 0, LCR_ERR_INVALID_ARG);  // torch.max over an empty dimension is an error too
+  if (N == 0) return LCR_OK;
+  LCR_REQUIRE(boxes && gt && max_iou && argmax, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(aligned_to(boxes, 16) && aligned_to(gt, 16), LCR_ERR_ALIGNMENT);
+  iou_kernel<false><<<(N + kIouThreads - 1) / kIouThreads, kIouThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(boxes), N, reinterpret_cast<const float4*>(gt), G, nullptr, max_iou,
+      reinterpret_cast<long long*>(argmax));
+  return after_launch();
+}
+
+extern "C" int lcr_mask_targets_f32(const uint8_t* gt_masks, int G, int H, int W, const float* boxes, const int64_t* gt_index,
+                                    int K, int M, float* out, void* stream) {
+  LCR_REQUIRE(K >= 0 && G >= 0 && H > 0 && W > 0 && M > 0, LCR_ERR_INVALID_ARG);
+  if (K == 0) return LCR_OK;
+  LCR_REQUIRE(gt_masks && boxes && out && G > 0, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(aligned_to(boxes, 16), LCR_ERR_ALIGNMENT);
+  LCR_REQUIRE((int64_t)H * W < (1ll << 31), LCR_ERR_CAPACITY);
+  mask_targets_kernel<<<K, 256, 0, as_stream(stream)>>>(gt_masks, G, H, W, reinterpret_cast<const float4*>(boxes),
+                                                       reinterpret_cast<const long long*>(gt_index), K, M, out);
+  return after_launch();
+}

@@ -1076,7 +1076,7 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
   const int groups = (p.C + WI::kChannels - 1) / WI::kChannels;
   const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<P>);
   const long long items = (long long)p.K * groups;
-  int ipw = 2;  // items per warp per CTA
+  int ipw = items >= (long long)WARPS * 2 * 4 * sm_count() ? 2 : 1;  // items per warp per CTA (small K: spread over all SMs)
   if (const char* v = getenv("LCR_ROI_IPW")) ipw = atoi(v);
   long long want = (items + WARPS - 1) / WARPS;
   if (ipw > 0) {
@@ -1108,7 +1108,7 @@ static int launch_bwd_warp(const RoiParams& p, const float* gout, cudaStream_t s
   const int groups = (p.C + WI::kChannels - 1) / WI::kChannels;
   const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<P>) + WARPS * 8;
   const long long items = (long long)p.K * groups;
-  const int ipw = 2;
+  const int ipw = items >= (long long)WARPS * 2 * 4 * sm_count() ? 2 : 1;
   const long long want = (items + (long long)WARPS * ipw - 1) / ((long long)WARPS * ipw);
   LCR_REQUIRE(want < (1ll << 31), LCR_ERR_CAPACITY);
   auto kern = roi_bwd_warp_kernel<P, WARPS, CSW>;

@@ -365,3 +365,54 @@ def pack_records(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor
             check(_lib.load().lcr_pack_records_f32(b.data_ptr(), s.data_ptr(), cn.data_ptr(), S, stride, rec.data_ptr(), _stream()),
                   "pack_records")
     return rec
+
+
+# ------------------------------------------------------------------------------------------------
+# training-side siblings
+def box_iou(boxes: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """torchvision.ops.box_iou (TV:ops/boxes.py:308-370): [N,4] x [G,4] -> [N,G], one kernel."""
+    _need_cuda(boxes, gt)
+    a, b = _f32c(boxes).reshape(-1, 4), _f32c(gt).reshape(-1, 4)
+    N, G = a.shape[0], b.shape[0]
+    out = torch.empty((N, G), dtype=torch.float32, device=a.device)
+    if N and G:
+        with torch.cuda.device(a.device):
+            check(_lib.load().lcr_box_iou_f32(a.data_ptr(), N, b.data_ptr(), G, out.data_ptr(), _stream()), "box_iou")
+    return out
+
+
+def box_iou_max(boxes: torch.Tensor, gt: torch.Tensor):
+    """Fused `box_iou(boxes, gt).max(dim=1)` (src/components/rpn.py:72-73, src/custom_maskrcnn.py:221-222):
+    (max_iou [N] f32, argmax [N] i64) without the [N,G] matrix."""
+    _need_cuda(boxes, gt)
+    a, b = _f32c(boxes).reshape(-1, 4), _f32c(gt).reshape(-1, 4)
+    N, G = a.shape[0], b.shape[0]
+    if G == 0:
+        raise _lib.LcrError("box_iou_max: no ground-truth boxes (torch.max over an empty dimension is an error too)")
+    mx = torch.empty((N,), dtype=torch.float32, device=a.device)
+    am = torch.empty((N,), dtype=torch.int64, device=a.device)
+    if N:
+        with torch.cuda.device(a.device):
+            check(_lib.load().lcr_box_iou_max_f32(a.data_ptr(), N, b.data_ptr(), G, mx.data_ptr(), am.data_ptr(), _stream()),
+                  "box_iou_max")
+    return mx, am
+
+
+def mask_targets(gt_masks: torch.Tensor, boxes: torch.Tensor, gt_index: Optional[torch.Tensor] = None, mask_size: int = 28) -> torch.Tensor:
+    """Batched extract_mask_target (src/utils/mask_utils.py:6-46): gt_masks [G,H,W] uint8, boxes [K,4],
+    gt_index [K] i64 (None: mask k) -> [K,M,M] f32 bilinear crops."""
+    _need_cuda(gt_masks, boxes, gt_index)
+    m = gt_masks if gt_masks.dtype == torch.uint8 else gt_masks.to(torch.uint8)
+    m = m.contiguous()
+    b = _f32c(boxes).reshape(-1, 4)
+    K = b.shape[0]
+    G, H, W = m.shape
+    idx = None if gt_index is None else gt_index.to(torch.int64).contiguous()
+    out = torch.empty((K, mask_size, mask_size), dtype=torch.float32, device=b.device)
+    if K:
+        if G == 0:
+            raise _lib.LcrError("mask_targets: no ground-truth masks")
+        with torch.cuda.device(b.device):
+            check(_lib.load().lcr_mask_targets_f32(m.data_ptr(), G, H, W, b.data_ptr(), _ptr(idx), K, int(mask_size), out.data_ptr(),
+                                                   _stream()), "mask_targets")
+    return out

@@ -20,6 +20,8 @@ from . import ops
 
 def convert_boxes_to_roi_format(boxes: Sequence[torch.Tensor]) -> torch.Tensor:
     """list[Tensor[K_i,4]] -> Tensor[K,5] with the image index in column 0 (TV:ops/_utils.py:18-25)."""
+    if len(boxes) == 1:   # the reference's call form (feature_map[b:b+1], [proposals]): one pad instead of full + 3 cats
+        return torch.nn.functional.pad(boxes[0], (1, 0), value=0.0)
     ids = [torch.full((b.shape[0], 1), float(i), dtype=b.dtype, device=b.device) for i, b in enumerate(boxes)]
     return torch.cat([torch.cat(ids, dim=0), torch.cat(list(boxes), dim=0)], dim=1)
 

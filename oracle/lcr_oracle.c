@@ -452,3 +452,72 @@ void orc_pack_records(const float* boxes, const float* scores, const int* counts
       }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * torchvision.ops.box_iou (TV:ops/boxes.py:308-370) + `.max(dim=1)`
+ * (src/components/rpn.py:72-73, src/custom_maskrcnn.py:221-222,249-250, src/utils/mask_utils.py:93-94).
+ * iou may be NULL (only the row max / argmax are wanted) and so may max_iou/argmax.
+ * ------------------------------------------------------------------------------------------- */
+void orc_box_iou(const float* boxes, int N, const float* gt, int G, float* iou, float* max_iou, int64_t* argmax) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < N; ++i) {
+    const float* a = boxes + (size_t)i * 4;
+    const float area_a = (a[2] - a[0]) * (a[3] - a[1]);
+    float best = 0.f;
+    int best_j = 0, have = 0, best_nan = 0;
+    for (int j = 0; j < G; ++j) {
+      const float* b = gt + (size_t)j * 4;
+      const float area_b = (b[2] - b[0]) * (b[3] - b[1]);
+      const float left = a[0] > b[0] ? a[0] : b[0], right = a[2] < b[2] ? a[2] : b[2];
+      const float top = a[1] > b[1] ? a[1] : b[1], bottom = a[3] < b[3] ? a[3] : b[3];
+      float w = right - left, h = bottom - top;
+      if (!(w > 0.f)) w = 0.f; /* clamp(min=0) */
+      if (!(h > 0.f)) h = 0.f;
+      const float inter = w * h;
+      const float v = inter / ((area_a + area_b) - inter);
+      if (iou) iou[(size_t)i * G + j] = v;
+      if (!best_nan && (!have || v > best || v != v)) { /* torch.max: first maximum; NaN propagates */
+        best = v;
+        best_j = j;
+        best_nan = (v != v);
+        have = 1;
+      }
+    }
+    if (max_iou) max_iou[i] = best;
+    if (argmax) argmax[i] = best_j;
+  }
+}
+
+/* extract_mask_target (src/utils/mask_utils.py:6-46) for K (box, mask index) pairs. */
+void orc_mask_targets(const uint8_t* gt_masks, int G, int H, int W, const float* boxes, const int64_t* gt_index, int K,
+                      int M, float* out) {
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int k = 0; k < K; ++k) {
+    float* o = out + (size_t)k * M * M;
+    const int64_t gi = gt_index ? gt_index[k] : k;
+    if (gi < 0 || gi >= G) {
+      memset(o, 0, sizeof(float) * M * M);
+      continue;
+    }
+    const float* b = boxes + (size_t)k * 4;
+    int x1 = (int)b[0], y1 = (int)b[1], x2 = (int)b[2], y2 = (int)b[3]; /* box.int(): truncation */
+    x1 = x1 < W - 1 ? x1 : W - 1; if (x1 < 0) x1 = 0;                    /* max(0, min(x1, w - 1)) */
+    y1 = y1 < H - 1 ? y1 : H - 1; if (y1 < 0) y1 = 0;
+    x2 = x2 < W ? x2 : W; if (x2 < x1 + 1) x2 = x1 + 1;                  /* max(x1 + 1, min(x2, w)) */
+    y2 = y2 < H ? y2 : H; if (y2 < y1 + 1) y2 = y1 + 1;
+    const int ch = y2 - y1, cw = x2 - x1;
+    const float sh = (float)ch / (float)M, sw = (float)cw / (float)M;
+    const uint8_t* m = gt_masks + (size_t)gi * H * W + (size_t)y1 * W + x1;
+    for (int oy = 0; oy < M; ++oy) {
+      int h0, h1; float wy0, wy1;
+      src_index(sh, oy, ch, &h0, &h1, &wy0, &wy1);
+      for (int ox = 0; ox < M; ++ox) {
+        int w0, w1; float wx0, wx1;
+        src_index(sw, ox, cw, &w0, &w1, &wx0, &wx1);
+        const float r0 = fmaf((float)m[(size_t)h0 * W + w0], wx0, (float)m[(size_t)h0 * W + w1] * wx1);
+        const float r1 = fmaf((float)m[(size_t)h1 * W + w0], wx0, (float)m[(size_t)h1 * W + w1] * wx1);
+        o[oy * M + ox] = fmaf(r0, wy0, r1 * wy1);
+      }
+    }
+  }
+}

@@ -234,3 +234,26 @@ def pack_records(boxes, scores, counts) -> np.ndarray:
     rec = np.zeros((S, stride, 6), np.float32)
     lib().orc_pack_records(_p(b), _p(s), _p(cn, C.c_int), C.c_int(S), C.c_int(stride), _p(rec))
     return rec
+
+
+def box_iou(boxes, gt, want_matrix=True):
+    """torchvision.ops.box_iou + `.max(dim=1)`.  Returns (iou [N,G] or None, max [N], argmax [N])."""
+    a, b = _f32(boxes).reshape(-1, 4), _f32(gt).reshape(-1, 4)
+    N, G = a.shape[0], b.shape[0]
+    iou = np.zeros((N, G), np.float32) if want_matrix else None
+    mx, am = np.zeros((N,), np.float32), np.zeros((N,), np.int64)
+    lib().orc_box_iou(_p(a), C.c_int(N), _p(b), C.c_int(G), _p(iou), _p(mx), _p(am, C.c_int64))
+    return iou, mx, am
+
+
+def mask_targets(gt_masks, boxes, gt_index=None, M=28) -> np.ndarray:
+    """extract_mask_target (src/utils/mask_utils.py:6-46) for K (box, mask index) pairs."""
+    m = np.ascontiguousarray(gt_masks, dtype=np.uint8)
+    G, H, W = m.shape
+    b = _f32(boxes).reshape(-1, 4)
+    K = b.shape[0]
+    idx = None if gt_index is None else np.ascontiguousarray(gt_index, dtype=np.int64)
+    out = np.zeros((K, M, M), np.float32)
+    lib().orc_mask_targets(_p(m, C.c_uint8), C.c_int(G), C.c_int(H), C.c_int(W), _p(b), _p(idx, C.c_int64), C.c_int(K), C.c_int(M),
+                           _p(out))
+    return out

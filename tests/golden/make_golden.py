@@ -27,9 +27,9 @@ from livecell_instance_segmentation_b200 import synth  # noqa: E402
 # --- the reference's own code (unmodified, imported from the read-only checkout) ---------------
 from src.components.anchor_generator import AnchorGenerator  # noqa: E402
 from src.utils.box_utils import clip_boxes_to_image, filter_small_boxes, encode_boxes  # noqa: E402
-from src.utils.mask_utils import paste_masks_in_image  # noqa: E402
+from src.utils.mask_utils import paste_masks_in_image, extract_mask_target  # noqa: E402
 from src.utils.proposal_utils import generate_inference_proposals, generate_training_proposals  # noqa: E402
-from torchvision.ops import RoIAlign, nms, MultiScaleRoIAlign  # noqa: E402  (what custom_maskrcnn.py:5 imports)
+from torchvision.ops import RoIAlign, nms, MultiScaleRoIAlign, box_iou  # noqa: E402  (what custom_maskrcnn.py:5 imports)
 from torchvision.ops.poolers import LevelMapper  # noqa: E402
 from torchvision.models.detection._utils import BoxCoder  # noqa: E402
 
@@ -215,7 +215,41 @@ def gen_pipeline():
     save("pipeline", **out)
 
 
+def gen_match():
+    """box_iou(...).max(dim=1) (src/components/rpn.py:72-73, src/custom_maskrcnn.py:221-222)
+    and extract_mask_target (src/utils/mask_utils.py:6-46), executed on CPU."""
+    rng = np.random.RandomState(91)
+    g = AnchorGenerator()
+    anc = g.generate_anchors((16, 20), 4, "cpu")                       # 2880 anchors of a 64x80 tile
+    gt = synth.make_det_boxes(12, 92, img_h=64, img_w=80, lo=8, hi=40)
+    gt[3] = gt[2]                                                      # duplicate box: argmax tie -> first index
+    gt[7] = [10.0, 10.0, 10.0, 10.0]                                   # zero-area gt
+    boxes = torch.cat([anc, T(np.array([[10.0, 10.0, 10.0, 10.0], [5.0, 5.0, 4.0, 4.0]], np.float32))])   # 0/0 and inverted
+    ious = box_iou(boxes, T(gt))
+    mx, am = ious.max(dim=1)
+    out = dict(boxes=boxes.numpy(), gt=gt, iou=ious.numpy(), max_iou=mx.numpy(), argmax=am.numpy())
+    # mask targets: rectangular + elliptical uint8 masks on a 64x80 tile, boxes incl. out-of-frame and sub-pixel ones
+    H, W, G = 64, 80, 6
+    yy, xx = np.mgrid[0:H, 0:W]
+    masks = np.zeros((G, H, W), np.uint8)
+    mb = synth.make_det_boxes(G, 93, img_h=H, img_w=W, lo=10, hi=36)
+    for i in range(G):
+        x1, y1, x2, y2 = mb[i]
+        cx, cy, rx, ry = (x1 + x2) / 2, (y1 + y2) / 2, max((x2 - x1) / 2, 1), max((y2 - y1) / 2, 1)
+        masks[i] = (((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2 <= 1.0) if i % 2 else ((xx >= x1) & (xx < x2) & (yy >= y1) & (yy < y2))
+    tb = np.concatenate([mb + rng.uniform(-3, 3, size=mb.shape).astype(np.float32), mb[:4] * 0.5,
+                         np.array([[-9.5, -4.0, 20.3, 30.9], [70.2, 50.1, 95.0, 80.0], [30.4, 20.2, 30.9, 20.7],
+                                   [79.6, 63.5, 85.0, 70.0]], np.float32)]).astype(np.float32)
+    idx = rng.randint(0, G, size=len(tb)).astype(np.int64)
+    tg = torch.stack([extract_mask_target(T(masks[i]), T(b), 28) for i, b in zip(idx, tb)])
+    out.update(masks=masks, t_boxes=tb, t_index=idx, targets=tg.numpy())
+    save("match", **out)
+
+
 if __name__ == "__main__":
+    gen_match() if "--only-match" in sys.argv else None
+    if "--only-match" in sys.argv:
+        sys.exit(0)
     gen_anchors()
     gen_box_utils()
     gen_proposals()
@@ -223,3 +257,4 @@ if __name__ == "__main__":
     gen_roi_align()
     gen_paste()
     gen_pipeline()
+    gen_match()

@@ -1,0 +1,82 @@
+"""GPU parity for the training-side siblings: box IoU / fused row max and batched
+mask targets, through the C-ABI, against the reference-generated golden vectors and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from livecell_instance_segmentation_b200 import ops as o
+    return o
+
+
+def test_box_iou_golden(ops, golden):
+    from gpu_util import N, T
+    g = golden("match")
+    iou = N(ops.box_iou(T(g["boxes"]), T(g["gt"])))
+    assert np.array_equal(iou, g["iou"], equal_nan=True)                 # bit-exact incl. NaN (0/0) and -0/+0 rows
+    mx, am = ops.box_iou_max(T(g["boxes"]), T(g["gt"]))
+    assert np.array_equal(N(mx), g["max_iou"], equal_nan=True)
+    assert np.array_equal(N(am), g["argmax"]) and am.dtype == torch.int64
+
+
+def test_box_iou_full_size_vs_oracle_and_torchvision(ops, oracle, synth):
+    """C1 geometry: 205 920 anchors x 160 ground-truth boxes (gt count spans two shared-memory chunks at 1500)."""
+    import torchvision
+    from gpu_util import N, T
+    anc = N(ops.anchors(130, 176, 4, ops.base_anchors(), "cuda:0"))
+    for G, seed in ((160, 3), (1500, 4)):
+        gt = synth.make_det_boxes(G, seed)
+        _, mx_ref, am_ref = oracle.box_iou(anc, gt, want_matrix=False)
+        mx, am = ops.box_iou_max(T(anc), T(gt))
+        assert np.array_equal(N(mx), mx_ref, equal_nan=True) and np.array_equal(N(am), am_ref)
+        tv_mx, tv_am = torchvision.ops.box_iou(T(anc), T(gt)).max(dim=1)
+        assert np.array_equal(N(mx), N(tv_mx), equal_nan=True)
+        # on exact ties the CUDA reduction of torch.max may pick another index: compare through the values
+        assert np.array_equal(N(torchvision.ops.box_iou(T(anc), T(gt)).gather(1, am[:, None])[:, 0]), N(tv_mx), equal_nan=True)
+    # thresholds used by the reference on top of the row max (rpn.py:75-76, custom_maskrcnn.py:225)
+    pos, neg = (mx >= 0.5), (mx < 0.3)
+    assert int(pos.sum()) == int((torch.from_numpy(mx_ref) >= 0.5).sum()) and int(neg.sum()) == int((torch.from_numpy(mx_ref) < 0.3).sum())
+
+
+def test_box_iou_edge_cases(ops):
+    from gpu_util import T
+    from livecell_instance_segmentation_b200._lib import LcrError
+    a = T(np.zeros((0, 4), np.float32))
+    g = T(np.array([[0, 0, 1, 1]], np.float32))
+    assert tuple(ops.box_iou(a, g).shape) == (0, 1)
+    mx, am = ops.box_iou_max(a, g)
+    assert mx.shape == (0,) and am.shape == (0,)
+    with pytest.raises(LcrError):
+        ops.box_iou_max(g, a)                       # no ground truth: torch.max over an empty dim raises too
+    with pytest.raises(LcrError):
+        ops.box_iou(g.cpu(), g.cpu())               # CPU tensors: no fallback
+
+
+def test_mask_targets_golden_and_oracle(ops, oracle, golden, synth):
+    from gpu_util import N, T
+    g = golden("match")
+    tg = N(ops.mask_targets(T(g["masks"]), T(g["t_boxes"]), T(g["t_index"]), 28))
+    np.testing.assert_allclose(tg, g["targets"], rtol=0, atol=1e-6)       # reference (ATen CPU bilinear)
+    assert np.array_equal(tg, oracle.mask_targets(g["masks"], g["t_boxes"], g["t_index"], 28))   # same expression tree
+    # full 704x520 frames, 300 positives matched to 40 cells, M = 28 and 14
+    rng = np.random.RandomState(5)
+    H, W, G, K = 520, 704, 40, 300
+    gb = synth.make_det_boxes(G, 6)
+    yy, xx = np.mgrid[0:H, 0:W]
+    masks = np.stack([((xx >= b[0]) & (xx < b[2]) & (yy >= b[1]) & (yy < b[3])).astype(np.uint8) for b in gb])
+    idx = rng.randint(0, G, size=K).astype(np.int64)
+    boxes = (gb[idx] + rng.uniform(-4, 4, size=(K, 4))).astype(np.float32)
+    for M in (28, 14):
+        out = N(ops.mask_targets(T(masks), T(boxes), T(idx), M))
+        assert np.array_equal(out, oracle.mask_targets(masks, boxes, idx, M))
+    # default index (target k <- mask k) and an out-of-range index (all zeros)
+    out = N(ops.mask_targets(T(masks), T(gb), None, 28))
+    assert np.array_equal(out, oracle.mask_targets(masks, gb, None, 28))
+    bad = idx.copy()
+    bad[7] = -1
+    out = N(ops.mask_targets(T(masks), T(boxes), T(bad), 28))
+    assert float(np.abs(out[7]).max()) == 0.0

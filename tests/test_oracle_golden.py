@@ -163,3 +163,20 @@ def test_pipeline_chain(golden, oracle, synth):
         probs = synth.make_mask_probs(60, 28, 65 + b)[: len(keep2)]
         masks = oracle.paste_masks(probs, props[keep2], 96, 128)
         assert np.array_equal(masks, g[f"det_masks_{b}"])
+
+
+def test_match_rows_golden(oracle, golden):
+    """the oracle's box_iou / row max and mask targets against the reference's
+    own outputs (torchvision.ops.box_iou(...).max(dim=1), extract_mask_target) — tests/golden/make_golden.py:gen_match."""
+    g = golden("match")
+    iou, mx, am = oracle.box_iou(g["boxes"], g["gt"])
+    assert np.array_equal(iou, g["iou"], equal_nan=True)            # same fp32 operations: bit-exact, NaN for 0/0
+    assert np.array_equal(mx, g["max_iou"], equal_nan=True)
+    assert np.array_equal(am, g["argmax"])
+    assert np.isnan(g["max_iou"]).any() and (g["argmax"] == 2).any()   # the fixture exercises NaN rows and the tie
+    _, mx2, am2 = oracle.box_iou(g["boxes"], g["gt"], want_matrix=False)
+    assert np.array_equal(mx2, mx, equal_nan=True) and np.array_equal(am2, am)
+    tg = oracle.mask_targets(g["masks"], g["t_boxes"], g["t_index"], 28)
+    assert tg.shape == g["targets"].shape
+    # ATen's CPU bilinear kernel is FMA-contracted differently per build (SURVEY App. B.4): values, not bits
+    np.testing.assert_allclose(tg, g["targets"], rtol=0, atol=1e-6)

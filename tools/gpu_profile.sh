@@ -5,9 +5,9 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain_bench.json 2> gpurun_out/plain_bench.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-# one whole timed step of the region kernels (7 matching launches per step; skip the 3 warm-up steps)
+# one whole timed step of the region kernels (8 matching launches per step; skip the 3 warm-up steps)
 ncu --set full --clock-control none --import-source on \
-    -k regex:"roi_fwd_nhwc|paste_rows16|rpn_select_kernel|nms_resolve|nms_mask" -s 21 -c 7 \
+    -k regex:"roi_fwd_warp|paste_bulk|rpn_prefilter|rpn_sortfilter|nms_resolve|nms_mask" -s 24 -c 8 \
     -f -o gpurun_out/prof_full $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out/

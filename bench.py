@@ -215,6 +215,7 @@ def run_ours(args):
     pipe = RegionPipeline(RegionConfig(pre_nms_top_n=PRE_NMS, post_nms_top_n=POST_NMS, max_detections=MAX_DET))
     stream = torch.cuda.current_stream()
     stage_names = ["rpn_select+nms+gather", "roi_align_fwd", "det_nms+gather", "paste+records"]
+    pending = []          # at most one in-flight all-gather of detection records
 
     def step(obj, feat, bs, probs, ev=None):
         if ev is not None:
@@ -231,8 +232,13 @@ def run_ours(args):
         det = pipe.paste(det, probs, (IMG_H, IMG_W), out=masks_d)
         if ev is not None:
             ev[4].record(stream)
-        rec, cnt = all_gather_detections(det.records, det.counts, n_items) if world > 1 else (det.records, det.counts)
-        return props, roi_feat, det, rec, cnt
+        # the only exchange: detection records (12 KB/frame).  Enqueued asynchronously; the previous step's gather is
+        # collected here, so the collective of step i overlaps the kernels of step i+1.
+        if world > 1:
+            if pending:
+                pending.pop().wait()
+            pending.append(all_gather_detections(det.records, det.counts, n_items, async_op=True))
+        return props, roi_feat, det, det.records, det.counts
 
     def barrier():
         if world > 1:
@@ -241,6 +247,8 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step(obj_d, feat_d, bs_d, probs_d)
+    if pending:
+        pending.pop().wait()
     barrier()
 
     # ---- timed region: inputs resident in HBM ----------------------------------------------------
@@ -254,6 +262,8 @@ def run_ours(args):
     t_start.record(stream)
     for i in range(args.steps):
         props, roi_feat, det, rec, cnt = step(obj_d, feat_d, bs_d, probs_d, evs[i])
+    if pending:
+        rec, cnt = pending.pop().wait()       # the last step's gathered records are part of the timed work
     t_end.record(stream)
     barrier()
     launches = _lib.launch_count() - l0

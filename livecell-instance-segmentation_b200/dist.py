@@ -27,27 +27,55 @@ def max_shard(n_items: int, world_size: int) -> int:
     return (n_items + world_size - 1) // world_size
 
 
-def all_gather_detections(records: torch.Tensor, counts: torch.Tensor, n_items: int, group=None):
+class GatherHandle:
+    """Pending all-gather of detection records; wait() makes the current stream wait and returns the tensors."""
+
+    def __init__(self, works, finish):
+        self._works, self._finish, self._result = works, finish, None
+
+    def wait(self):
+        if self._result is None:
+            for w in self._works:
+                w.wait()
+            self._result = self._finish()
+        return self._result
+
+
+def all_gather_detections(records: torch.Tensor, counts: torch.Tensor, n_items: int, group=None, async_op: bool = False):
     """records [n_local, D, 6] f32, counts [n_local] i32 of this rank's shard  ->
     (records [n_items, D, 6], counts [n_items]) identical on every rank, in global image order.
-    Shards are padded to the largest shard so the collective has a fixed size."""
+    Shards are padded to the largest shard so the collective has a fixed size.  With async_op the two
+    collectives are only enqueued (NCCL's own stream): the caller keeps launching the next batch and calls
+    .wait() on the returned GatherHandle when it needs the result — the records are 12 KB/frame, so the
+    exchange then costs nothing on the critical path."""
     if not dist.is_initialized():
-        return records, counts
+        return GatherHandle([], lambda: (records, counts)) if async_op else (records, counts)
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
     cap = max_shard(n_items, world)
     n_local, D = records.shape[0], records.shape[1]
-    rec = records.new_zeros((cap, D, 6))
-    cnt = counts.new_zeros((cap,))
-    rec[:n_local] = records
-    cnt[:n_local] = counts
+    even = n_items == world * cap and n_local == cap
+    if even:
+        rec, cnt = records.contiguous(), counts.contiguous()
+    else:
+        rec = records.new_zeros((cap, D, 6))
+        cnt = counts.new_zeros((cap,))
+        rec[:n_local] = records
+        cnt[:n_local] = counts
     out_rec = records.new_empty((world * cap, D, 6))
     out_cnt = counts.new_empty((world * cap,))
-    dist.all_gather_into_tensor(out_rec, rec, group=group)
-    dist.all_gather_into_tensor(out_cnt, cnt, group=group)
-    recs, cnts = [], []
-    for r in range(world):
-        s, e = shard_range(n_items, r, world)
-        recs.append(out_rec[r * cap: r * cap + (e - s)])
-        cnts.append(out_cnt[r * cap: r * cap + (e - s)])
-    return torch.cat(recs, dim=0), torch.cat(cnts, dim=0)
+    works = [dist.all_gather_into_tensor(out_rec, rec, group=group, async_op=async_op),
+             dist.all_gather_into_tensor(out_cnt, cnt, group=group, async_op=async_op)]
+
+    def finish():
+        if even:
+            return out_rec, out_cnt
+        recs, cnts = [], []
+        for r in range(world):
+            s, e = shard_range(n_items, r, world)
+            recs.append(out_rec[r * cap: r * cap + (e - s)])
+            cnts.append(out_cnt[r * cap: r * cap + (e - s)])
+        return torch.cat(recs, dim=0), torch.cat(cnts, dim=0)
+
+    if async_op:
+        return GatherHandle(works, finish)
+    return finish()

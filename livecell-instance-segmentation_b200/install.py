@@ -29,11 +29,15 @@ PATCHES = {
         "clip_boxes_to_image": _bu.clip_boxes_to_image,
         "filter_small_boxes": _bu.filter_small_boxes,
     },
-    "src.utils.mask_utils": {"paste_masks_in_image": _mu.paste_masks_in_image},
+    "src.utils.mask_utils": {"paste_masks_in_image": _mu.paste_masks_in_image, "extract_mask_target": _mu.extract_mask_target,
+                             "compute_mask_loss_from_gt": _mu.compute_mask_loss_from_gt, "box_iou": _ra.box_iou},
+    "src.components.rpn": {"box_iou": _ra.box_iou},
     "src.custom_maskrcnn": {
         "AnchorGenerator": _ag.AnchorGenerator,
         "RoIAlign": _ra.RoIAlign,
         "nms": _ra.nms,
+        "box_iou": _ra.box_iou,
+        "compute_mask_loss_from_gt": _mu.compute_mask_loss_from_gt,
         "generate_training_proposals": _pu.generate_training_proposals,
         "generate_inference_proposals": _pu.generate_inference_proposals,
         "sample_proposals": _pu.sample_proposals,

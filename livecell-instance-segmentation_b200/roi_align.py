@@ -6,7 +6,8 @@
 * ``nms`` / ``batched_nms`` — same signatures and return type (int64 kept indices, score order).
 * ``MultiScaleRoIAlign`` — the multi-level pooler of the transfer model (TV:ops/poolers.py:230-321),
   level assignment + all levels in ONE launch.
-``box_iou`` is loss-side (SURVEY §8f "next") and stays torchvision's.
+* ``box_iou`` / ``box_iou_max`` — the IoU matrix in one kernel, and the fused ``box_iou(a, b).max(dim=1)``
+  every loss-side call site computes next.
 """
 from __future__ import annotations
 
@@ -152,3 +153,13 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, i
     keep, kc = ops.nms_batched(boxes.reshape(1, n, 4), scores.reshape(1, n), float(iou_threshold), post_n=n,
                                category=idxs.reshape(1, n))
     return keep[0, : int(kc.item())].clone()
+
+
+def box_iou(boxes1: torch.Tensor, boxes2: torch.Tensor) -> torch.Tensor:
+    """torchvision.ops.box_iou drop-in (TV:ops/boxes.py:308-370): [N,4] x [M,4] -> [N,M]."""
+    return ops.box_iou(boxes1, boxes2)
+
+
+def box_iou_max(boxes1: torch.Tensor, boxes2: torch.Tensor):
+    """(values, indices) of ``box_iou(boxes1, boxes2).max(dim=1)`` without materialising the matrix."""
+    return ops.box_iou_max(boxes1, boxes2)

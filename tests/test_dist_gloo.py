@@ -36,16 +36,23 @@ def _worker(rank, world, port, n_items, q):
     s, e = shard_range(n_items, rank, world)
     rec, cnt = _fake_detect(list(range(s, e)))
     grec, gcnt = all_gather_detections(rec, cnt, n_items)
+    h = all_gather_detections(rec, cnt, n_items, async_op=True)       # the overlapped form bench.py uses
+    arec, acnt = h.wait()
+    assert torch.equal(arec, grec) and torch.equal(acnt, gcnt) and h.wait()[0] is arec
     q.put((rank, grec.numpy(), gcnt.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_two_rank_gather_equals_single_process():
+    _run_world(7, 2)                           # ragged shards: 4 + 3 (padded collective)
+    _run_world(6, 2)                           # even shards: the gathered buffer is returned as is
+
+
+def _run_world(n_items, world):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
-    n_items, world = 7, 2                      # ragged shards: 4 + 3
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -66,3 +73,5 @@ def test_single_process_passthrough():
     rec, cnt = _fake_detect([0, 1, 2])
     r2, c2 = all_gather_detections(rec, cnt, 3)
     assert r2 is rec and c2 is cnt
+    r3, c3 = all_gather_detections(rec, cnt, 3, async_op=True).wait()
+    assert r3 is rec and c3 is cnt

@@ -80,3 +80,38 @@ def test_mask_targets_golden_and_oracle(ops, oracle, golden, synth):
     bad[7] = -1
     out = N(ops.mask_targets(T(masks), T(boxes), T(bad), 28))
     assert float(np.abs(out[7]).max()) == 0.0
+
+
+def test_mask_loss_shim_matches_reference_formula(ops, synth):
+    """compute_mask_loss_from_gt (mask_utils.py:49-126) through the shim == the reference's formula evaluated with
+    torch/torchvision ops on the same device (IoU match > 0.3, per-positive bilinear targets, BCE on class 1)."""
+    import torch.nn.functional as F
+    import torchvision
+    from gpu_util import T
+    from livecell_instance_segmentation_b200.src.utils.mask_utils import compute_mask_loss_from_gt, extract_mask_target
+    rng = np.random.RandomState(17)
+    H, W, G, K = 256, 256, 12, 96
+    gb = synth.make_det_boxes(G, 18, img_h=H, img_w=W, lo=20, hi=50)
+    yy, xx = np.mgrid[0:H, 0:W]
+    masks = np.stack([((xx >= b[0]) & (xx < b[2]) & (yy >= b[1]) & (yy < b[3])).astype(np.uint8) for b in gb])
+    props = np.concatenate([gb[rng.randint(0, G, size=K // 2)] + rng.uniform(-5, 5, size=(K // 2, 4)),
+                            synth.make_det_boxes(K // 2, 19, img_h=H, img_w=W, lo=20, hi=50)]).astype(np.float32)
+    logits = T(rng.standard_normal((K, 2, 28, 28)).astype(np.float32))
+    targets = [{"boxes": T(gb[:7]), "masks": T(masks[:7]), "labels": torch.ones(7)},
+               {"boxes": T(gb[7:]), "masks": T(masks[7:]), "labels": torch.ones(G - 7)}]
+    loss = compute_mask_loss_from_gt(logits, T(props), targets, "cuda:0")
+    # the reference formula, with ATen/torchvision CUDA ops
+    ious = torchvision.ops.box_iou(T(props), T(gb))
+    mx, idx = ious.max(dim=1)
+    pos = mx > 0.3
+    assert int(pos.sum()) > 10
+    tg = []
+    for gi in idx[pos].tolist():
+        x1, y1, x2, y2 = [int(v) for v in gb[gi]]
+        x1 = max(0, min(x1, W - 1)); y1 = max(0, min(y1, H - 1)); x2 = max(x1 + 1, min(x2, W)); y2 = max(y1 + 1, min(y2, H))
+        crop = T(masks[gi])[y1:y2, x1:x2].float()[None, None]
+        tg.append(F.interpolate(crop, size=(28, 28), mode="bilinear", align_corners=False)[0, 0])
+    ref = F.binary_cross_entropy_with_logits(logits[pos][:, 1], torch.stack(tg), reduction="mean")
+    assert abs(float(loss) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
+    t1 = extract_mask_target(T(masks[3]), T(gb[3]), 28)
+    assert tuple(t1.shape) == (28, 28)

@@ -43,6 +43,9 @@ def test_shim_signatures_mirror_the_reference():
     assert [p.default for p in list(sig.parameters.values())[4:]] == [500, 0.01, 5]
     assert inspect.signature(pu.sample_proposals).parameters["num_samples"].default == 128
     assert list(inspect.signature(mu.paste_masks_in_image).parameters) == ["masks", "boxes", "image_size", "threshold"]
+    assert list(inspect.signature(mu.extract_mask_target).parameters) == ["gt_mask", "box", "mask_size"]
+    assert list(inspect.signature(mu.compute_mask_loss_from_gt).parameters) == ["mask_logits", "proposals", "targets", "device", "mask_size"]
+    assert inspect.signature(mu.compute_mask_loss_from_gt).parameters["mask_size"].default == 28
     assert inspect.signature(bu.filter_small_boxes).parameters["min_size"].default == 1
     g = AnchorGenerator()
     assert (g.sizes, g.aspect_ratios, g.num_anchors_per_location) == ((32, 64, 128), (0.5, 1.0, 2.0), 9)
@@ -68,7 +71,7 @@ def test_install_rebinds_reference_names(monkeypatch):
     monkeypatch.setitem(sys.modules, "src.custom_maskrcnn", fake)
     monkeypatch.setitem(sys.modules, "custom_maskrcnn", fake)
     done = inst.install(import_missing=False)
-    assert fake.RoIAlign is ra.RoIAlign and fake.nms is ra.nms and fake.box_iou == "untouched"
+    assert fake.RoIAlign is ra.RoIAlign and fake.nms is ra.nms and fake.box_iou is ra.box_iou   # §8f rank 1: one-kernel IoU
     assert "CustomMaskRCNN._generate_masks" in done["src.custom_maskrcnn"]
     assert CustomMaskRCNN._generate_masks is inst._paste_method
 

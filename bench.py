@@ -190,7 +190,13 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on the process's stdout; the contract is ONE JSON line there, so fd 1 is
+        # pointed at stderr until the result line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     F = args.frames
     n_items = F * world
@@ -395,6 +401,9 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_baseline(16, 3, 1)
             line["cpu_baseline"] = cb
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

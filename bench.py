@@ -223,28 +223,41 @@ def run_ours(args):
     stage_names = ["rpn_select+nms+gather", "roi_align_fwd", "det_nms+gather", "paste+records"]
     pending = []          # at most one in-flight all-gather of detection records
 
-    def step(obj, feat, bs, probs, ev=None):
-        if ev is not None:
-            ev[0].record(stream)
-        props = pipe.proposals(obj, (IMG_H, IMG_W))
-        if ev is not None:
-            ev[1].record(stream)
-        roi_feat = pipe.pool(feat, props.rois, out=roi_out_d)
-        if ev is not None:
-            ev[2].record(stream)
-        det = pipe.detections(props, bs)
-        if ev is not None:
-            ev[3].record(stream)
-        det = pipe.paste(det, probs, (IMG_H, IMG_W), out=masks_d)
+    # one pass of the region path over the rank's F frames = four stages, ~12 launches of liblcr kernels, no host sync
+    def stage_fns(obj, feat, bs, probs):
+        st = {}
+
+        def s1():
+            st["props"] = pipe.proposals(obj, (IMG_H, IMG_W))
+
+        def s2():
+            st["roi_feat"] = pipe.pool(feat, st["props"].rois, out=roi_out_d)
+
+        def s3():
+            st["det"] = pipe.detections(st["props"], bs)
+
+        def s4():
+            st["det"] = pipe.paste(st["det"], probs, (IMG_H, IMG_W), out=masks_d)
+
+        return [s1, s2, s3, s4], st
+
+    def step_eager(ev=None):
+        fns, st = stage_fns(obj_d, feat_d, bs_d, probs_d)
+        for j, fn in enumerate(fns):
+            if ev is not None:
+                ev[j].record(stream)
+            fn()
         if ev is not None:
             ev[4].record(stream)
+        return st
+
+    def gather(det):
         # the only exchange: detection records (12 KB/frame).  Enqueued asynchronously; the previous step's gather is
-        # collected here, so the collective of step i overlaps the kernels of step i+1.
+        # collected first, so the collective of step i overlaps the kernels of step i+1.
         if world > 1:
             if pending:
                 pending.pop().wait()
             pending.append(all_gather_detections(det.records, det.counts, n_items, async_op=True))
-        return props, roi_feat, det, det.records, det.counts
 
     def barrier():
         if world > 1:
@@ -252,27 +265,66 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step(obj_d, feat_d, bs_d, probs_d)
+        gather(step_eager()["det"])
     if pending:
         pending.pop().wait()
     barrier()
+    l0 = _lib.launch_count()
+    st = step_eager()
+    launches_per_step = _lib.launch_count() - l0
+    barrier()
+
+    # ---- the step as CUDA graphs: the C-ABI launches are stream-ordered and sync-free, so a serving loop captures
+    # them once and replays; the timed region then measures the device, not the Python launch path.  One graph per
+    # stage so that events between the replays give the per-stage times of the SAME timed steps.  Two sets with
+    # separate result buffers alternate when N > 1, so the async all-gather of step i never races step i+1.
+    graph_sets, launch_mode = [], "cuda_graph_replay (4 stage graphs per step)"
+    if args.no_graph:
+        launch_mode = "eager"
+    else:
+        try:
+            for _ in range(2 if world > 1 else 1):
+                fns, gst = stage_fns(obj_d, feat_d, bs_d, probs_d)
+                gs = []
+                for fn in fns:
+                    gph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gph):
+                        fn()
+                    gs.append(gph)
+                graph_sets.append((gs, gst))
+            for gs, _ in graph_sets:
+                for gph in gs:
+                    gph.replay()
+            barrier()
+        except Exception as exc:          # capture unsupported for some reason: time the eager launches instead
+            print(f"bench: CUDA graph capture failed ({exc!r}); timing eager launches", file=sys.stderr)
+            graph_sets, launch_mode = [], "eager"
+            torch.cuda.synchronize()
 
     # ---- timed region: inputs resident in HBM ----------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
-    l0 = _lib.launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record(stream)
     for i in range(args.steps):
-        props, roi_feat, det, rec, cnt = step(obj_d, feat_d, bs_d, probs_d, evs[i])
+        if graph_sets:
+            gs, st = graph_sets[i % len(graph_sets)]
+            for j, gph in enumerate(gs):
+                evs[i][j].record(stream)
+                gph.replay()
+            evs[i][4].record(stream)
+        else:
+            st = step_eager(evs[i])
+        gather(st["det"])
     if pending:
         rec, cnt = pending.pop().wait()       # the last step's gathered records are part of the timed work
     t_end.record(stream)
     barrier()
-    launches = _lib.launch_count() - l0
+    props, roi_feat, det = st["props"], st["roi_feat"], st["det"]
+    launches = launches_per_step * args.steps
     ms_step = t_start.elapsed_time(t_end) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -358,6 +410,7 @@ def run_ours(args):
     # ---- e2e: the public host-fed entry point (pipeline.HostFedRegionPipeline.run): every step copies that
     # step's inputs from pinned host memory (chunked, overlapped with compute) and reads the records back ----------
     from livecell_instance_segmentation_b200.pipeline import HostFedRegionPipeline
+    graph_sets = st = None
     del masks_d, roi_out_d, roi_feat, det, props
     torch.cuda.empty_cache()
     runner = HostFedRegionPipeline(RegionConfig(pre_nms_top_n=PRE_NMS, post_nms_top_n=POST_NMS, max_detections=MAX_DET), F,
@@ -395,7 +448,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms, "api": f"pipeline.HostFedRegionPipeline.run (chunks of {runner.FC} frames, H2D overlapped with compute)",
                     "d2h": "detection records + counts (pasted masks stay sharded in HBM, SURVEY §8e)",
                     "counts_match_resident_run": e2e_ok},
-            "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "nms_us_2000_boxes": nms_us, "nms_us_2000_boxes_eager": nms_us_eager,
+            "gpu_launches": int(launches), "launch_mode": launch_mode, "roofline": roofline, "kernels": kernels, "nms_us_2000_boxes": nms_us, "nms_us_2000_boxes_eager": nms_us_eager,
             "proposals_per_frame": n_props / F, "detections_per_frame": n_det / F,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -419,6 +472,7 @@ def main():
     ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--chunk-frames", type=int, default=8, help="e2e: frames per H2D/compute pipeline chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager Python launches instead of CUDA-graph replays")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

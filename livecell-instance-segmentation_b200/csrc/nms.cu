@@ -204,10 +204,13 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, in
 // Warp 0 owns the serial part (greedy pass over the chunk's 32x32 diagonal block: the 32 diagonal
 // words are broadcast with shuffles up front, the dependent chain is two LOP3 per box); all warps
 // then OR the rows of the kept boxes into the `removed` bit-vector (lane = row, warp = word slot,
-// independent loads + redux.sync: one L2 round trip per chunk instead of one per kept row).
+// redux.sync).  The row words are loaded one chunk ahead of the greedy pass, speculatively for all 32
+// rows, so no L2 round trip sits on the per-chunk critical path.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxWords = LCR_MAX_NMS_BOXES / 32;
-constexpr int kResolveThreads = 256;
+constexpr int kResolveThreads = 512;
+constexpr int kResolveWarps = kResolveThreads / 32;
+constexpr int kResolveWpt = 4;  // mask words per thread held in registers (covers 16*4 = 64 words = 2048 boxes per pass)
 
 __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int stride, int post_n, NmsWorkspace ws,
                                                                       int64_t* __restrict__ keep, int* __restrict__ keep_counts) {
@@ -222,16 +225,30 @@ __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int stride
   int64_t* out = keep + (size_t)s * post_n;
 
   for (int w = tid; w < nchunks; w += kResolveThreads) removed[w] = 0u;
-  __syncthreads();
   int count = 0;
-  uint32_t diag = (warp == 0 && nchunks > 0 && lane < n) ? mask[(size_t)lane * nw] : 0u;
+  uint32_t diag = (warp == 0 && nchunks > 0 && lane < n) ? __ldg(mask + (size_t)lane * nw) : 0u;
+
+  // Row words of chunk c for this thread (lane = row of the chunk, warp = word slot): issued one chunk AHEAD,
+  // before the kept set is known, so the L2 round trip overlaps the serial greedy pass of warp 0.
+  auto prefetch = [&](int c, uint32_t (&v)[kResolveWpt]) {
+    const int row = min((c << 5) + lane, n - 1);  // rows past n: clamped, their kept bit is 0
+    const uint32_t* mrow = mask + (size_t)row * nw;
+#pragma unroll
+    for (int j = 0; j < kResolveWpt; ++j) {
+      const int w = c + 1 + warp + j * kResolveWarps;
+      v[j] = (c < nchunks && w < nchunks) ? __ldg(mrow + w) : 0u;
+    }
+  };
+  uint32_t v[kResolveWpt];
+  prefetch(0, v);
+  __syncthreads();
 
   for (int c = 0; c < nchunks && count < post_n; ++c) {
     const int row0 = c << 5;
     if (warp == 0) {
       // prefetch the next chunk's diagonal word (address is data-independent)
       const int nrow = row0 + 32 + lane;
-      const uint32_t diag_next = (c + 1 < nchunks && nrow < n) ? mask[(size_t)nrow * nw + (c + 1)] : 0u;
+      const uint32_t diag_next = (c + 1 < nchunks && nrow < n) ? __ldg(mask + (size_t)nrow * nw + (c + 1)) : 0u;
       const int left = n - row0;
       const uint32_t in_range = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
       uint32_t alive = ~removed[c] & in_range;
@@ -256,26 +273,23 @@ __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int stride
     __syncthreads();
     const uint32_t kept = s_kept;
     count += __popc(kept);
-    if (count < post_n) {  // block-uniform
-      // lane = row of the chunk, warp = word slot: every thread issues at most four independent loads
-      // (one L2 round trip per chunk), rows are OR-reduced across the warp with redux.sync
-      const bool row_kept = (kept >> lane) & 1u;                       // implies row0 + lane < n
-      const uint32_t* mrow = mask + (size_t)(row0 + lane) * nw;
-      for (int w0 = c + 1 + warp; w0 < nchunks; w0 += 4 * (kResolveThreads / 32)) {
-        uint32_t v[4];
+    uint32_t vn[kResolveWpt];
+    prefetch(c + 1, vn);  // in flight while this chunk is folded and the next greedy pass runs
+    const bool row_kept = (kept >> lane) & 1u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int w = w0 + j * (kResolveThreads / 32);
-          v[j] = (row_kept && w < nchunks) ? __ldg(mrow + w) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int w = w0 + j * (kResolveThreads / 32);
-          const uint32_t acc = __reduce_or_sync(0xFFFFFFFFu, v[j]);
-          if (lane == 0 && w < nchunks) removed[w] |= acc;
-        }
-      }
+    for (int j = 0; j < kResolveWpt; ++j) {
+      const int w = c + 1 + warp + j * kResolveWarps;
+      const uint32_t acc = __reduce_or_sync(0xFFFFFFFFu, row_kept ? v[j] : 0u);
+      if (lane == 0 && w < nchunks) removed[w] |= acc;
     }
+    // segments longer than 2048 boxes: the remaining words of the kept rows, loaded on demand
+    for (int w0 = c + 1 + warp + kResolveWpt * kResolveWarps; w0 < nchunks; w0 += kResolveWarps) {
+      const uint32_t x = row_kept ? __ldg(mask + (size_t)(row0 + lane) * nw + w0) : 0u;
+      const uint32_t acc = __reduce_or_sync(0xFFFFFFFFu, x);
+      if (lane == 0) removed[w0] |= acc;
+    }
+#pragma unroll
+    for (int j = 0; j < kResolveWpt; ++j) v[j] = vn[j];
     __syncthreads();
   }
   if (tid == 0) keep_counts[s] = min(count, post_n);

@@ -249,6 +249,25 @@ int lcr_box_iou_max_f32(const float* boxes, int N, const float* gt, int G, float
 int lcr_mask_targets_f32(const uint8_t* gt_masks, int G, int H, int W, const float* boxes,
                          const int64_t* gt_index, int K, int M, float* out, void* stream);
 
+/* Mask-head tail.  Replaces the F.interpolate(mask_logits, (M,M), bilinear,
+ * align_corners=False) that ends CustomMaskHead.forward (src/components/mask_head.py:52-58) and the
+ * sigmoid(mask_logits[:, 1]) of _generate_masks (src/custom_maskrcnn.py:273-274): class `cls` only,
+ * upsample + sigmoid in one pass.  logits [K, num_classes, m, m] f32 -> probs [K, M, M] f32
+ * (the input format of lcr_paste_masks_u8).  m == M skips the resize. */
+int lcr_mask_tail_f32(const float* logits, int K, int num_classes, int cls, int m, int M, float* probs,
+                      void* stream);
+
+/* Tile stitching.  Replaces calculate_mask_area_in_region (src/visualize.py:106-130)
+ * inside filter_detections_by_border_mini_tiles (:174-257): for detection i, total[i] = #{mask > threshold}
+ * and, for each of its rectangles r in rects[rect_offsets[i] .. rect_offsets[i+1]) (at most 16;
+ * (x0,y0,x1,y1) half-open, mask coordinates, already clipped to the frame), in_region[r] = the number of
+ * those pixels inside r.  Exact integer counts; the float64 fractions and the > mask_threshold decision stay
+ * with the caller, as in the reference.  boxes [N,4] (optional): the detection boxes the masks were pasted
+ * with — only the box area is scanned.  masks [N,H,W] u8. */
+int lcr_mask_region_counts_u8(const uint8_t* masks, int N, int H, int W, const float* boxes,
+                              const int* rects, const int* rect_offsets, int threshold, int* total,
+                              int* in_region, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

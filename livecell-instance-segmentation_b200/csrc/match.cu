@@ -121,6 +121,89 @@ __global__ void __launch_bounds__(256) mask_targets_kernel(const uint8_t* __rest
   }
 }
 
+// ---- mask-head tail -----------------------------------------------------------
+// CustomMaskHead.forward ends with F.interpolate(mask_logits [K,2,m,m] -> [K,2,M,M], bilinear,
+// align_corners=False) (src/components/mask_head.py:52-58) and _generate_masks then takes
+// sigmoid(mask_logits[:, 1]) (src/custom_maskrcnn.py:273-274): three passes over [K,2,28,28] of which half
+// is thrown away.  One kernel: class `cls` only, upsample + sigmoid fused, output = the paste kernel's input.
+__global__ void __launch_bounds__(256) mask_tail_kernel(const float* __restrict__ logits, int K, int Cc, int cls, int m, int M,
+                                                        float* __restrict__ probs) {
+  const int k = blockIdx.x;
+  const float* src = logits + ((size_t)k * Cc + cls) * m * m;
+  float* o = probs + (size_t)k * M * M;
+  const float scale = __fdiv_rn((float)m, (float)M);
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+    const int oy = i / M, ox = i - oy * M;
+    float v;
+    if (m == M) {
+      v = __ldg(src + i);
+    } else {
+      int h0, h1, w0, w1;
+      float wy0, wy1, wx0, wx1;
+      src_index_mt(scale, oy, m, h0, h1, wy0, wy1);
+      src_index_mt(scale, ox, m, w0, w1, wx0, wx1);
+      const float a = __ldg(src + h0 * m + w0), b = __ldg(src + h0 * m + w1);
+      const float c = __ldg(src + h1 * m + w0), d = __ldg(src + h1 * m + w1);
+      const float top = __fmaf_rn(a, wx0, __fmul_rn(b, wx1));
+      const float bot = __fmaf_rn(c, wx0, __fmul_rn(d, wx1));
+      v = __fmaf_rn(top, wy0, __fmul_rn(bot, wy1));
+    }
+    o[i] = sigmoid_f32(v);
+  }
+}
+
+// ---- tile stitching -----------------------------------------------------------
+// calculate_mask_area_in_region (src/visualize.py:106-130) as used by
+// filter_detections_by_border_mini_tiles (:174-257): per detection, the number of mask pixels inside each
+// of its valid mini-tile rectangles and in the whole mask.  Integer counts out (exact); the float64
+// fractions and the threshold stay on the host exactly as the reference computes them.
+// One CTA per detection; when boxes are given only the box rows/columns are scanned (a pasted mask is zero
+// outside its box).
+constexpr int kMaxRects = 16;
+
+__global__ void __launch_bounds__(256) mask_region_counts_kernel(const uint8_t* __restrict__ masks, int N, int H, int W,
+                                                                 const float4* __restrict__ boxes, const int4* __restrict__ rects,
+                                                                 const int* __restrict__ rect_offsets, int thr,
+                                                                 int* __restrict__ total, int* __restrict__ in_region) {
+  __shared__ int s_cnt[kMaxRects + 1];
+  __shared__ int4 s_rect[kMaxRects];
+  const int i = blockIdx.x;
+  const int r0 = rect_offsets[i], nr = min(rect_offsets[i + 1] - r0, kMaxRects);
+  if (threadIdx.x <= kMaxRects) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x < nr) s_rect[threadIdx.x] = rects[r0 + threadIdx.x];
+  __syncthreads();
+  int x1 = 0, y1 = 0, x2 = W, y2 = H;
+  if (boxes) {  // same integer box as the paste kernel wrote into (src/custom_maskrcnn.py:279-283)
+    const float4 b = __ldg(boxes + i);
+    x1 = max(0, __float2int_rz(b.x));
+    y1 = max(0, __float2int_rz(b.y));
+    x2 = min(W, __float2int_rz(b.z));
+    y2 = min(H, __float2int_rz(b.w));
+  }
+  const uint8_t* mk = masks + (size_t)i * H * W;
+  const int bw = max(x2 - x1, 0), bh = max(y2 - y1, 0);
+  int cnt[kMaxRects + 1];
+#pragma unroll
+  for (int r = 0; r <= kMaxRects; ++r) cnt[r] = 0;
+  for (int p = threadIdx.x; p < bw * bh; p += blockDim.x) {
+    const int y = y1 + p / bw, x = x1 + p % bw;
+    if ((int)mk[(size_t)y * W + x] > thr) {
+      cnt[0]++;
+#pragma unroll
+      for (int r = 0; r < kMaxRects; ++r)
+        if (r < nr && x >= s_rect[r].x && x < s_rect[r].z && y >= s_rect[r].y && y < s_rect[r].w) cnt[r + 1]++;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r <= kMaxRects; ++r) {
+    const int v = __reduce_add_sync(0xFFFFFFFFu, cnt[r]);
+    if (lane_id() == 0 && v) atomicAdd(&s_cnt[r], v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) total[i] = s_cnt[0];
+  if (threadIdx.x < nr) in_region[r0 + threadIdx.x] = s_cnt[threadIdx.x + 1];
+}
+
 }  // namespace lcr
 
 using namespace lcr;
@@ -156,5 +239,27 @@ extern "C" int lcr_mask_targets_f32(const uint8_t* gt_masks, int G, int H, int W
   LCR_REQUIRE((int64_t)H * W < (1ll << 31), LCR_ERR_CAPACITY);
   mask_targets_kernel<<<K, 256, 0, as_stream(stream)>>>(gt_masks, G, H, W, reinterpret_cast<const float4*>(boxes),
                                                        reinterpret_cast<const long long*>(gt_index), K, M, out);
+  return after_launch();
+}
+
+extern "C" int lcr_mask_tail_f32(const float* logits, int K, int num_classes, int cls, int m, int M, float* probs, void* stream) {
+  LCR_REQUIRE(K >= 0 && num_classes > 0 && cls >= 0 && cls < num_classes && m > 0 && M > 0, LCR_ERR_INVALID_ARG);
+  if (K == 0) return LCR_OK;
+  LCR_REQUIRE(logits && probs, LCR_ERR_INVALID_ARG);
+  mask_tail_kernel<<<K, 256, 0, as_stream(stream)>>>(logits, K, num_classes, cls, m, M, probs);
+  return after_launch();
+}
+
+extern "C" int lcr_mask_region_counts_u8(const uint8_t* masks, int N, int H, int W, const float* boxes, const int* rects,
+                                         const int* rect_offsets, int threshold, int* total, int* in_region, void* stream) {
+  LCR_REQUIRE(N >= 0 && H > 0 && W > 0, LCR_ERR_INVALID_ARG);
+  if (N == 0) return LCR_OK;
+  LCR_REQUIRE(masks && rect_offsets && total, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(!boxes || aligned_to(boxes, 16), LCR_ERR_ALIGNMENT);
+  LCR_REQUIRE(!rects || aligned_to(rects, 16), LCR_ERR_ALIGNMENT);
+  LCR_REQUIRE((int64_t)H * W < (1ll << 31), LCR_ERR_CAPACITY);
+  mask_region_counts_kernel<<<N, 256, 0, as_stream(stream)>>>(masks, N, H, W, reinterpret_cast<const float4*>(boxes),
+                                                             reinterpret_cast<const int4*>(rects), rect_offsets, threshold, total,
+                                                             in_region);
   return after_launch();
 }

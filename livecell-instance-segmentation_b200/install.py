@@ -54,9 +54,26 @@ def _paste_method(self, roi_features, boxes, image_size, device):
     img_h, img_w = image_size
     if len(boxes) == 0:
         return torch.zeros((0, img_h, img_w), dtype=torch.uint8, device=device)
-    mask_logits = self.mask_head(roi_features)
-    mask_probs = torch.sigmoid(mask_logits[:, 1])
+    mask_probs = mask_head_probs(self.mask_head, roi_features)
     return _mu.paste_masks_in_image(mask_probs, boxes, (img_h, img_w), threshold=0.5)
+
+
+_HEAD_LAYERS = ("conv1", "conv2", "conv3", "conv4", "deconv", "deconv_relu", "mask_fcn_logits")
+
+
+def mask_head_probs(mask_head, roi_features):
+    """sigmoid(mask_head(x)[:, 1]) with the head's tail fused: the reference head's own layers
+    (src/components/mask_head.py:41-50, weights untouched) produce the 14x14 logits; the final bilinear 14->28 of both
+    classes + class select + sigmoid (mask_head.py:52-58, custom_maskrcnn.py:273-274) become one kernel over class 1.
+    A head without those attributes is simply called, and only the sigmoid/select is fused."""
+    from . import ops
+    if all(hasattr(mask_head, n) for n in _HEAD_LAYERS) and hasattr(mask_head, "mask_size"):
+        x = roi_features
+        for n in _HEAD_LAYERS:
+            x = getattr(mask_head, n)(x)
+        return ops.mask_tail(x, int(mask_head.mask_size), 1)
+    logits = mask_head(roi_features)
+    return ops.mask_tail(logits, int(logits.shape[-1]), 1)
 
 
 def install(import_missing: bool = True) -> dict:

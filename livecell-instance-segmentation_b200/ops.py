@@ -416,3 +416,41 @@ def mask_targets(gt_masks: torch.Tensor, boxes: torch.Tensor, gt_index: Optional
             check(_lib.load().lcr_mask_targets_f32(m.data_ptr(), G, H, W, b.data_ptr(), _ptr(idx), K, int(mask_size), out.data_ptr(),
                                                    _stream()), "mask_targets")
     return out
+
+
+def mask_tail(mask_logits: torch.Tensor, mask_size: int = 28, cls: int = 1) -> torch.Tensor:
+    """Fused tail of the mask head: bilinear (align_corners=False) resize of class `cls` of
+    mask_logits [K,num_classes,m,m] to mask_size + sigmoid -> probs [K,mask_size,mask_size]
+    (src/components/mask_head.py:52-58 + src/custom_maskrcnn.py:273-274)."""
+    _need_cuda(mask_logits)
+    x = _f32c(mask_logits)
+    K, Cc, m, m2 = x.shape
+    if m != m2:
+        raise _lib.LcrError("mask_tail: square mask logits expected")
+    out = torch.empty((K, mask_size, mask_size), dtype=torch.float32, device=x.device)
+    if K:
+        with torch.cuda.device(x.device):
+            check(_lib.load().lcr_mask_tail_f32(x.data_ptr(), K, Cc, int(cls), m, int(mask_size), out.data_ptr(), _stream()), "mask_tail")
+    return out
+
+
+def mask_region_counts(masks: torch.Tensor, rects: torch.Tensor, rect_offsets: torch.Tensor, boxes: Optional[torch.Tensor] = None,
+                       threshold: int = 0):
+    """Per-detection pixel counts for tile stitching (src/visualize.py:106-130): masks [N,H,W] uint8,
+    rects [R,4] int32 (x0,y0,x1,y1 half-open, clipped), rect_offsets [N+1] int32 -> (total [N] i32, in_region [R] i32)."""
+    _need_cuda(masks, rects, rect_offsets, boxes)
+    if masks.dtype != torch.uint8:
+        raise _lib.LcrError("mask_region_counts: uint8 masks expected")
+    m = masks.contiguous()
+    N, H, W = m.shape
+    r = rects.to(torch.int32).contiguous().reshape(-1, 4)
+    ro = rect_offsets.to(torch.int32).contiguous()
+    b = None if boxes is None else _f32c(boxes).reshape(-1, 4)
+    total = torch.zeros((N,), dtype=torch.int32, device=m.device)
+    inreg = torch.zeros((max(r.shape[0], 1),), dtype=torch.int32, device=m.device)
+    if N:
+        with torch.cuda.device(m.device):
+            check(_lib.load().lcr_mask_region_counts_u8(m.data_ptr(), N, H, W, _ptr(b), r.data_ptr() if r.numel() else None, ro.data_ptr(),
+                                                        int(threshold), total.data_ptr(), inreg.data_ptr(), _stream()),
+                  "mask_region_counts")
+    return total, inreg[: r.shape[0]]

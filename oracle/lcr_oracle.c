@@ -521,3 +521,47 @@ void orc_mask_targets(const uint8_t* gt_masks, int G, int H, int W, const float*
     }
   }
 }
+
+/* tail of CustomMaskHead.forward (src/components/mask_head.py:52-58: bilinear
+ * resize of the logits, align_corners=False) + sigmoid of class `cls` (src/custom_maskrcnn.py:273-274). */
+void orc_mask_tail(const float* logits, int K, int num_classes, int cls, int m, int M, float* probs) {
+  const float scale = (float)m / (float)M;
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < K; ++k) {
+    const float* src = logits + ((size_t)k * num_classes + cls) * m * m;
+    float* o = probs + (size_t)k * M * M;
+    for (int oy = 0; oy < M; ++oy)
+      for (int ox = 0; ox < M; ++ox) {
+        float v;
+        if (m == M) {
+          v = src[oy * m + ox];
+        } else {
+          int h0, h1, w0, w1; float wy0, wy1, wx0, wx1;
+          src_index(scale, oy, m, &h0, &h1, &wy0, &wy1);
+          src_index(scale, ox, m, &w0, &w1, &wx0, &wx1);
+          const float r0 = fmaf(src[h0 * m + w0], wx0, src[h0 * m + w1] * wx1);
+          const float r1 = fmaf(src[h1 * m + w0], wx0, src[h1 * m + w1] * wx1);
+          v = fmaf(r0, wy0, r1 * wy1);
+        }
+        o[oy * M + ox] = sigmoidf_(v);
+      }
+  }
+}
+
+/* the pixel counts behind calculate_mask_area_in_region (src/visualize.py:106-130). */
+void orc_mask_region_counts(const uint8_t* masks, int N, int H, int W, const int* rects, const int* rect_offsets,
+                            int threshold, int* total, int* in_region) {
+  for (int i = 0; i < N; ++i) {
+    const uint8_t* m = masks + (size_t)i * H * W;
+    int t = 0;
+    for (int p = 0; p < H * W; ++p) t += ((int)m[p] > threshold);
+    total[i] = t;
+    for (int r = rect_offsets[i]; r < rect_offsets[i + 1]; ++r) {
+      const int* q = rects + (size_t)r * 4;
+      int c = 0;
+      for (int y = q[1]; y < q[3]; ++y)
+        for (int x = q[0]; x < q[2]; ++x) c += ((int)m[(size_t)y * W + x] > threshold);
+      in_region[r] = c;
+    }
+  }
+}

@@ -257,3 +257,24 @@ def mask_targets(gt_masks, boxes, gt_index=None, M=28) -> np.ndarray:
     lib().orc_mask_targets(_p(m, C.c_uint8), C.c_int(G), C.c_int(H), C.c_int(W), _p(b), _p(idx, C.c_int64), C.c_int(K), C.c_int(M),
                            _p(out))
     return out
+
+
+def mask_tail(logits, M=28, cls=1) -> np.ndarray:
+    """Bilinear resize of class `cls` of logits [K,Cc,m,m] to MxM + sigmoid."""
+    x = _f32(logits)
+    K, Cc, m, _ = x.shape
+    out = np.zeros((K, M, M), np.float32)
+    lib().orc_mask_tail(_p(x), C.c_int(K), C.c_int(Cc), C.c_int(cls), C.c_int(m), C.c_int(M), _p(out))
+    return out
+
+
+def mask_region_counts(masks, rects, rect_offsets, threshold=0):
+    """Pixel counts per detection and per rectangle."""
+    m = np.ascontiguousarray(masks, dtype=np.uint8)
+    N, H, W = m.shape
+    r = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 4)
+    ro = np.ascontiguousarray(rect_offsets, dtype=np.int32)
+    total, inreg = np.zeros((N,), np.int32), np.zeros((max(len(r), 1),), np.int32)
+    lib().orc_mask_region_counts(_p(m, C.c_uint8), C.c_int(N), C.c_int(H), C.c_int(W), _p(r, C.c_int), _p(ro, C.c_int),
+                                 C.c_int(threshold), _p(total, C.c_int), _p(inreg, C.c_int))
+    return total, inreg[: len(r)]

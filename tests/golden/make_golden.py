@@ -246,9 +246,70 @@ def gen_match():
     save("match", **out)
 
 
+def _import_reference_visualize():
+    """src/visualize.py needs matplotlib / pycocotools at import time (not installed here): stub them —
+    the functions executed below (tile geometry + mask-area filter, visualize.py:100-257) use neither."""
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "pycocotools", "pycocotools.mask"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].patches = sys.modules["matplotlib.patches"]
+    sys.modules["pycocotools"].mask = sys.modules["pycocotools.mask"]
+    import importlib
+    return importlib.import_module("src.visualize")
+
+
+def gen_tail_stitch():
+    """SURVEY §8(f) ranks 3-4.  (3) the tail of the reference mask head: CustomMaskHead.forward's final
+    F.interpolate (src/components/mask_head.py:52-58) is executed through the reference module itself (the convs are
+    bypassed by feeding mask_fcn_logits' output) + sigmoid(mask_logits[:, 1]) (src/custom_maskrcnn.py:273-274).
+    (4) filter_detections_by_border_mini_tiles (src/visualize.py:174-257) on 25 synthetic tile predictions."""
+    import torch.nn.functional as F
+    from src.components.mask_head import CustomMaskHead
+    rng = np.random.RandomState(97)
+    head = CustomMaskHead()
+    logits14 = rng.standard_normal((9, 2, 14, 14)).astype(np.float32) * 2
+    # the head's own tail: everything before it replaced by identities so forward(x) == interpolate(x)
+    ident = torch.nn.Identity()
+    for name in ("conv1", "conv2", "conv3", "conv4", "deconv", "deconv_relu", "mask_fcn_logits"):
+        setattr(head, name, ident)
+    up = head(T(logits14))
+    assert tuple(up.shape) == (9, 2, 28, 28)
+    probs = torch.sigmoid(up[:, 1])
+    out = dict(logits14=logits14, probs28=probs.numpy())
+    logits28 = rng.standard_normal((3, 2, 28, 28)).astype(np.float32)
+    out.update(logits28=logits28, probs28_same=torch.sigmoid(head(T(logits28))[:, 1]).numpy())
+
+    viz = _import_reference_visualize()
+    th, tw = 3 * (viz.IMG_HEIGHT // viz.N_MINI_ROWS), 3 * (viz.IMG_WIDTH // viz.N_MINI_COLS)     # 222 x 300 tiles
+    results, packed = [], {}
+    for t in range(viz.TOTAL_TILES):
+        n = 14
+        boxes = synth.make_det_boxes(n, 200 + t, img_h=th, img_w=tw, lo=14, hi=60)
+        probs_t = synth.make_mask_probs(n, 28, 300 + t)
+        masks = paste_masks_in_image(T(probs_t), T(boxes), (th, tw)).numpy()
+        scores = rng.uniform(0.2, 1.0, size=n).astype(np.float32)
+        results.append({"tile_num": t, "prediction": {"boxes": T(boxes), "scores": T(scores), "masks": T(masks)}})
+        packed[f"t{t}_boxes"], packed[f"t{t}_scores"], packed[f"t{t}_masks_bits"] = boxes, scores, np.packbits(masks > 0)
+    kept = viz.filter_detections_by_border_mini_tiles(list(reversed(results)), score_threshold=0.5, mask_threshold=0.4)
+    assert len(kept) > 20
+    out.update(packed)
+    out.update(tile_hw=np.array([th, tw]), n_per_tile=np.array(14),
+               kept_tile=np.array([d["tile_num"] for d in kept]), kept_box=np.array([d["box"] for d in kept], np.float64),
+               kept_score=np.array([d["score"] for d in kept], np.float64),
+               kept_fraction=np.array([d["area_fraction"] for d in kept], np.float64),
+               kept_mask_sum=np.array([int(d["mask"].sum()) for d in kept]),
+               valid_mini_tiles=np.array([len(viz.get_valid_mini_tiles_for_tile(t)) for t in range(viz.TOTAL_TILES)]))
+    save("tail_stitch", **out)
+
+
 if __name__ == "__main__":
-    gen_match() if "--only-match" in sys.argv else None
     if "--only-match" in sys.argv:
+        gen_match()
+        sys.exit(0)
+    if "--only-tail-stitch" in sys.argv:
+        gen_tail_stitch()
         sys.exit(0)
     gen_anchors()
     gen_box_utils()
@@ -258,3 +319,4 @@ if __name__ == "__main__":
     gen_paste()
     gen_pipeline()
     gen_match()
+    gen_tail_stitch()

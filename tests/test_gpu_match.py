@@ -115,3 +115,65 @@ def test_mask_loss_shim_matches_reference_formula(ops, synth):
     assert abs(float(loss) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
     t1 = extract_mask_target(T(masks[3]), T(gb[3]), 28)
     assert tuple(t1.shape) == (28, 28)
+
+
+def test_mask_tail_golden_and_oracle(ops, oracle, golden):
+    from gpu_util import N, T
+    g = golden("tail_stitch")
+    p = N(ops.mask_tail(T(g["logits14"]), 28, 1))
+    np.testing.assert_allclose(p, g["probs28"], rtol=0, atol=1e-6)             # reference head tail + sigmoid
+    np.testing.assert_allclose(p, oracle.mask_tail(g["logits14"], 28, 1), rtol=0, atol=2e-7)   # glibc vs CUDA expf
+    np.testing.assert_allclose(N(ops.mask_tail(T(g["logits28"]), 28, 1)), g["probs28_same"], rtol=0, atol=1e-6)
+    assert tuple(ops.mask_tail(T(np.zeros((0, 2, 14, 14), np.float32))).shape) == (0, 28, 28)
+    # the fused tail feeds the paste kernel exactly like the unfused chain (thresholded masks identical)
+    import torch.nn.functional as F
+    rng = np.random.RandomState(4)
+    logits = T((rng.standard_normal((40, 2, 14, 14)) * 3).astype(np.float32))
+    from livecell_instance_segmentation_b200 import synth
+    boxes = T(synth.make_det_boxes(40, 9))
+    unfused = torch.sigmoid(F.interpolate(logits, size=(28, 28), mode="bilinear", align_corners=False)[:, 1])
+    a = ops.paste_masks(ops.mask_tail(logits, 28, 1), boxes, 520, 704)
+    b = ops.paste_masks(unfused, boxes, 520, 704)
+    assert float((a != b).float().mean()) < 1e-6       # ulp-level probability differences may flip a pixel sitting on 0.5
+
+
+def test_tile_stitch_filter_matches_reference(golden):
+    """stitch.filter_detections_by_border_mini_tiles on GPU-resident predictions == the reference's own
+    filter_detections_by_border_mini_tiles (visualize.py:174-257) executed on CPU (fixture: 25 tiles x 14 detections)."""
+    from gpu_util import T
+    from test_oracle_golden import _stitch_results
+    from livecell_instance_segmentation_b200 import stitch
+    g = golden("tail_stitch")
+    results = [{"tile_num": r["tile_num"], "prediction": {"boxes": T(r["boxes"]), "scores": T(r["scores"]), "masks": T(r["masks"])}}
+               for r in _stitch_results(g)]
+    kept = stitch.filter_detections_by_border_mini_tiles(list(reversed(results)), score_threshold=0.5, mask_threshold=0.4)
+    assert [d["tile_num"] for d in kept] == g["kept_tile"].tolist()
+    assert np.array_equal(np.array([d["area_fraction"] for d in kept]), g["kept_fraction"])     # float64 bit-exact
+    assert np.array_equal(np.array([d["score"] for d in kept]), g["kept_score"])
+    np.testing.assert_allclose(np.array([d["box"] for d in kept]), g["kept_box"], rtol=0, atol=1e-4)
+    assert [int(d["mask"].sum()) for d in kept] == g["kept_mask_sum"].tolist()
+    assert kept[0]["mask"].is_cuda and kept[0]["mask"].dtype == torch.bool
+    # float probability masks [N,1,h,w] (the transfer model's output format) take the same path
+    res2 = [{"tile_num": r["tile_num"], "prediction": {"boxes": r["prediction"]["boxes"], "scores": r["prediction"]["scores"],
+                                                       "masks": (r["prediction"]["masks"].float() / 255.0)[:, None]}} for r in results]
+    kept2 = stitch.filter_detections_by_border_mini_tiles(res2)
+    assert [d["tile_num"] for d in kept2] == g["kept_tile"].tolist()
+
+
+def test_mask_region_counts_with_boxes(ops, oracle, synth):
+    """Scanning only the box area gives the same counts as the whole frame (a pasted mask is zero outside its box)."""
+    from gpu_util import N, T
+    n, H, W = 50, 520, 704
+    boxes = synth.make_det_boxes(n, 12, edge_cases=True)
+    masks = ops.paste_masks(T(synth.make_mask_probs(n, 28, 13)), T(boxes), H, W)
+    rng = np.random.RandomState(3)
+    R = 5
+    x0, y0 = rng.randint(0, W - 50, size=(n, R)), rng.randint(0, H - 50, size=(n, R))
+    rects = np.stack([x0, y0, x0 + rng.randint(1, 300, size=(n, R)), y0 + rng.randint(1, 300, size=(n, R))], axis=-1)
+    rects[..., 2] = np.minimum(rects[..., 2], W)
+    rects[..., 3] = np.minimum(rects[..., 3], H)
+    ro = np.arange(0, (n + 1) * R, R)
+    t_ref, r_ref = oracle.mask_region_counts(N(masks), rects.reshape(-1, 4), ro)
+    for bx in (None, T(boxes)):
+        t, r = ops.mask_region_counts(masks, T(rects.reshape(-1, 4).astype(np.int32)), T(ro.astype(np.int32)), boxes=bx)
+        assert np.array_equal(N(t), t_ref) and np.array_equal(N(r), r_ref)

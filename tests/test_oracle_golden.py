@@ -180,3 +180,51 @@ def test_match_rows_golden(oracle, golden):
     assert tg.shape == g["targets"].shape
     # ATen's CPU bilinear kernel is FMA-contracted differently per build: values, not bits
     np.testing.assert_allclose(tg, g["targets"], rtol=0, atol=1e-6)
+
+
+def _stitch_results(g):
+    th, tw = [int(v) for v in g["tile_hw"]]
+    n = int(g["n_per_tile"])
+    res = []
+    for t in range(25):
+        masks = (np.unpackbits(g[f"t{t}_masks_bits"])[: n * th * tw].reshape(n, th, tw) * 255).astype(np.uint8)
+        res.append(dict(tile_num=t, boxes=g[f"t{t}_boxes"], scores=g[f"t{t}_scores"], masks=masks))
+    return res
+
+
+def test_tail_and_stitch_rows_golden(oracle, golden):
+    """the oracle's mask-head tail against the reference head's own interpolate + sigmoid, and its
+    pixel counts driving the reference's tile filter (visualize.py:174-257) to the reference's kept set."""
+    g = golden("tail_stitch")
+    np.testing.assert_allclose(oracle.mask_tail(g["logits14"], 28, 1), g["probs28"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(oracle.mask_tail(g["logits28"], 28, 1), g["probs28_same"], rtol=0, atol=1e-6)
+    from livecell_instance_segmentation_b200 import stitch
+    assert [len(stitch.get_valid_mini_tiles_for_tile(t)) for t in range(25)] == g["valid_mini_tiles"].tolist()
+    # host logic of stitch.py with the oracle's counts in place of the kernel's
+    mtw, mth = 704 // 7, 520 // 7
+    kept, processed = [], set()
+    for r in _stitch_results(g):
+        t = r["tile_num"]
+        cs, rs = stitch.get_tile_position_in_grid(t)
+        ox, oy = cs * mtw, rs * mth
+        new = [mt for mt in stitch.get_valid_mini_tiles_for_tile(t) if mt not in processed]
+        if not new:
+            continue
+        k = r["scores"] > 0.5
+        masks, boxes, scores = r["masks"][k], r["boxes"][k], r["scores"][k]
+        h, w = masks.shape[1:]
+        rects = [[max(0, mc * mtw - ox), max(0, mr * mth - oy), min(w, mc * mtw + mtw - ox), min(h, mr * mth + mth - oy)] for mc, mr in new]
+        live = [q[0] < q[2] and q[1] < q[3] for q in rects]
+        rects = [q if ok else [0, 0, 0, 0] for q, ok in zip(rects, live)]
+        n, R = len(boxes), len(rects)
+        total, inreg = oracle.mask_region_counts(masks, np.tile(np.array(rects, np.int32), (n, 1)), np.arange(0, (n + 1) * R, R))
+        inreg = inreg.reshape(n, R)
+        for i in range(n):
+            frac = sum((int(inreg[i, q]) / int(total[i])) if (live[q] and total[i] > 0) else 0.0 for q in range(R))
+            if frac > 0.4:
+                kept.append((t, frac, float(scores[i]), [boxes[i][0] + ox, boxes[i][1] + oy, boxes[i][2] + ox, boxes[i][3] + oy]))
+        processed.update(new)
+    assert [k[0] for k in kept] == g["kept_tile"].tolist()
+    assert np.array_equal(np.array([k[1] for k in kept]), g["kept_fraction"])          # float64, same summation order
+    assert np.array_equal(np.array([k[2] for k in kept]), g["kept_score"])
+    np.testing.assert_allclose(np.array([k[3] for k in kept]), g["kept_box"], rtol=0, atol=1e-4)

@@ -190,6 +190,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from livecell_instance_segmentation_b200.dist import bind_to_gpu_numa_node
+    numa_cores = bind_to_gpu_numa_node(local) if world > 1 else []     # before the pinned host buffers are allocated
     saved_stdout = None
     if world > 1:
         # NCCL prints its version banner on the process's stdout; the contract is ONE JSON line there, so fd 1 is
@@ -447,7 +449,7 @@ def run_ours(args):
             "e2e": {"value": n_items / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "api": f"pipeline.HostFedRegionPipeline.run (chunks of {runner.FC} frames, H2D overlapped with compute)",
                     "d2h": "detection records + counts (pasted masks stay sharded in HBM, SURVEY §8e)",
-                    "counts_match_resident_run": e2e_ok},
+                    "counts_match_resident_run": e2e_ok, "host_cores_bound_to_gpu_numa_node": len(numa_cores)},
             "gpu_launches": int(launches), "launch_mode": launch_mode, "roofline": roofline, "kernels": kernels, "nms_us_2000_boxes": nms_us, "nms_us_2000_boxes_eager": nms_us_eager,
             "proposals_per_frame": n_props / F, "detections_per_frame": n_det / F,
         }

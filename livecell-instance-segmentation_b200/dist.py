@@ -14,6 +14,34 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int) -> list:
+    """Pin this process to the CPU cores NVML reports as local to GPU `device_index` (restricted to the cores the
+    process may use), so that pinned host buffers are first-touched on the GPU's own NUMA node and the host->device
+    copies of 8 ranks do not cross the socket interconnect.  Returns the core list ([] when nothing was changed)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                idx = int(ids[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        local = {i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        cores = sorted(local & allowed)
+        if cores and len(cores) < len(allowed):
+            os.sched_setaffinity(0, cores)
+            return cores
+    except Exception:
+        pass
+    return []
+
+
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous block [start, end) of rank `rank`; blocks differ in size by at most one item."""
     if world_size <= 0 or not (0 <= rank < world_size):

@@ -126,7 +126,10 @@ __device__ __forceinline__ void paste_bulk_store(void* gdst, const void* ssrc, u
                : "memory");
 }
 __device__ __forceinline__ void paste_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void paste_bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void paste_bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void paste_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // bilinear + threshold with the probabilities staged in shared memory (same expression tree as paste_pixel)
@@ -149,13 +152,13 @@ constexpr int kPasteRB = 11 * 1024;   // one row chunk (16 rows of a 704-px fram
 
 __global__ void __launch_bounds__(kPasteThreads) paste_bulk_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
                                                                    const uint8_t* __restrict__ valid, int N, int M, int H, int W,
-                                                                   float thr, uint32_t on_value, uint8_t* __restrict__ out) {
+                                                                   float thr, uint32_t on_value, uint8_t* __restrict__ out, int zb_bytes) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint8_t* zb = smem;
-  uint8_t* rb = smem + kPasteZB;                                               // two chunks of kPasteRB bytes
-  float* sprob = reinterpret_cast<float*>(smem + kPasteZB + 2 * kPasteRB);    // [M*M]
+  uint8_t* rb = smem + zb_bytes;                                               // two chunks of kPasteRB bytes
+  float* sprob = reinterpret_cast<float*>(smem + zb_bytes + 2 * kPasteRB);    // [M*M]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < kPasteZB / 16; i += kPasteThreads) reinterpret_cast<uint4*>(zb)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < zb_bytes / 16; i += kPasteThreads) reinterpret_cast<uint4*>(zb)[i] = make_uint4(0u, 0u, 0u, 0u);
   paste_fence_async();
   __syncthreads();
   uint64_t pol;
@@ -164,67 +167,79 @@ __global__ void __launch_bounds__(kPasteThreads) paste_bulk_kernel(const float* 
   const int chunk_rows = max(1, min(kPasteRB / W, H));
   const int MM = M * M;
   int buf = 0;
+  // Bulk-group bookkeeping (thread 0): groups complete in commit order; a row chunk may be recomposed once the group
+  // that stored it has finished READING shared memory.  The zero-row stores of a frame are committed LAST, in their
+  // own group, so they never sit between a chunk and its reuse: the copy engine drains them in the background.
+  int seq = 0;                      // groups committed so far
+  int last_use[2] = {-1, -1};       // group id of each chunk buffer's latest store
 
   for (int det = blockIdx.x; det < N; det += gridDim.x) {
     if (valid && !valid[det]) continue;  // block-uniform
     const PasteBox pb = make_paste_box(boxes, det, M, H, W);
     uint8_t* frame = out + (size_t)det * H * W;
     const int y1 = pb.live ? pb.y1 : 0, y2 = pb.live ? pb.y2 : 0;
-    if (tid == 0) {  // rows [0, y1) and [y2, H) are zeros: bulk stores from the zero buffer, joined to the next commit
+    if (pb.live) {
+      // the previous frame's readers of sprob passed the barrier that followed their last chunk
+      const float* prob = probs + (size_t)det * MM;
+      for (int i = tid; i < MM; i += kPasteThreads) sprob[i] = __ldg(prob + i);
+      for (int yc = y1; yc < y2; yc += chunk_rows) {
+        const int rows = min(chunk_rows, y2 - yc);
+        uint8_t* chunk = rb + buf * kPasteRB;
+        if (tid == 0) {  // groups younger than this buffer's last store may stay pending
+          const int pending_ok = seq - 1 - last_use[buf];
+          if (pending_ok <= 0) paste_bulk_wait_read<0>();
+          else if (pending_ok == 1) paste_bulk_wait_read<1>();
+          else if (pending_ok == 2) paste_bulk_wait_read<2>();
+          else paste_bulk_wait_read<3>();
+        }
+        __syncthreads();                         // (also publishes sprob)
+        for (int r = warp; r < rows; r += kPasteThreads / 32) {
+          int h0, h1;
+          float wy0, wy1;
+          src_index(pb.sh, yc + r - pb.y1, M, h0, h1, wy0, wy1);
+          for (int xv = lane; xv < vpr; xv += 32) {
+            const int x0 = xv * 16;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (x0 < pb.x2 && x0 + 16 > pb.x1) {
+              uint32_t w[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t word = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int x = x0 + q * 4 + j;
+                  if (x >= pb.x1 && x < pb.x2 && paste_pixel_smem(sprob, M, h0, h1, wy0, wy1, pb.sw, x - pb.x1, thr))
+                    word |= on_value << (8 * j);
+                }
+                w[q] = word;
+              }
+              v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4*>(chunk + (size_t)r * W + x0) = v;
+          }
+        }
+        paste_fence_async();
+        __syncthreads();
+        if (tid == 0) {
+          paste_bulk_store(frame + (size_t)yc * W, chunk, (uint32_t)(rows * W), pol);
+          paste_bulk_commit();
+          last_use[buf] = seq++;
+        }
+        buf ^= 1;
+      }
+    }
+    if (tid == 0) {  // rows [0, y1) and [y2, H) are zeros: bulk stores straight from the zero buffer, one group
       for (int part = 0; part < 2; ++part) {
         size_t a = part == 0 ? 0 : (size_t)y2 * W;
         const size_t b = part == 0 ? (size_t)y1 * W : (size_t)H * W;
         while (a < b) {
-          const uint32_t n = (uint32_t)min((size_t)kPasteZB, b - a);
+          const uint32_t n = (uint32_t)min((size_t)zb_bytes, b - a);
           paste_bulk_store(frame + a, zb, n, pol);
           a += n;
         }
       }
-    }
-    if (!pb.live) {
-      if (tid == 0) paste_bulk_commit();
-      continue;
-    }
-    // the previous frame's readers of sprob passed the barrier that followed their last chunk
-    const float* prob = probs + (size_t)det * MM;
-    for (int i = tid; i < MM; i += kPasteThreads) sprob[i] = __ldg(prob + i);
-    for (int yc = y1; yc < y2; yc += chunk_rows) {
-      const int rows = min(chunk_rows, y2 - yc);
-      uint8_t* chunk = rb + buf * kPasteRB;
-      if (tid == 0) paste_bulk_wait_read_1();  // the store issued two chunks ago has finished reading this buffer
-      __syncthreads();                         // (also publishes sprob)
-      for (int r = warp; r < rows; r += kPasteThreads / 32) {
-        int h0, h1;
-        float wy0, wy1;
-        src_index(pb.sh, yc + r - pb.y1, M, h0, h1, wy0, wy1);
-        for (int xv = lane; xv < vpr; xv += 32) {
-          const int x0 = xv * 16;
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (x0 < pb.x2 && x0 + 16 > pb.x1) {
-            uint32_t w[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t word = 0u;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int x = x0 + q * 4 + j;
-                if (x >= pb.x1 && x < pb.x2 && paste_pixel_smem(sprob, M, h0, h1, wy0, wy1, pb.sw, x - pb.x1, thr))
-                  word |= on_value << (8 * j);
-              }
-              w[q] = word;
-            }
-            v = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-          *reinterpret_cast<uint4*>(chunk + (size_t)r * W + x0) = v;
-        }
-      }
-      paste_fence_async();
-      __syncthreads();
-      if (tid == 0) {
-        paste_bulk_store(frame + (size_t)yc * W, chunk, (uint32_t)(rows * W), pol);
-        paste_bulk_commit();
-      }
-      buf ^= 1;
+      paste_bulk_commit();
+      ++seq;
     }
   }
   if (tid == 0) paste_bulk_wait_all();
@@ -270,8 +285,11 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
   const int vpr = W / 16;
   const bool fast = (W % 16 == 0) && aligned_to(out, 16) && vpr <= 512;
   const char* mode = getenv("LCR_PASTE");  // tuning switch for A/B runs: "rows16" selects the per-thread store kernel
-  const size_t bulk_smem = (size_t)kPasteZB + 2 * kPasteRB + round_up(sizeof(float) * (size_t)M * M, 16);
-  if (fast && W <= kPasteRB && bulk_smem <= 100 * 1024 && !(mode && strcmp(mode, "rows16") == 0)) {
+  int zb_bytes = kPasteZB;
+  if (const char* v = getenv("LCR_PASTE_ZB_KB")) zb_bytes = atoi(v) * 1024;   // tuning switch
+  if (zb_bytes < 1024 || zb_bytes > 128 * 1024 || zb_bytes % 1024) zb_bytes = kPasteZB;
+  const size_t bulk_smem = (size_t)zb_bytes + 2 * kPasteRB + round_up(sizeof(float) * (size_t)M * M, 16);
+  if (fast && W <= kPasteRB && bulk_smem <= 200 * 1024 && !(mode && strcmp(mode, "rows16") == 0)) {
     static thread_local int configured_dev = -1;
     static thread_local size_t configured_smem = 0;
     int dev = 0;
@@ -286,7 +304,7 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
     const long long max_blocks = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
     const int blocks = (int)((long long)N < max_blocks ? N : max_blocks);
     paste_bulk_kernel<<<blocks, kPasteThreads, bulk_smem, as_stream(stream)>>>(probs, boxes, valid, N, M, H, W, threshold,
-                                                                              (uint32_t)on_value, out);
+                                                                              (uint32_t)on_value, out, zb_bytes);
     return after_launch();
   }
   if (fast) {

@@ -388,15 +388,15 @@ struct __align__(16) AxisTapB {
   float w_lo, w_hi;
 };
 
-constexpr int kXB = 7;  // x-bins per lane
+constexpr int kPadBins = 16;  // table capacity in x-bins (halves * bins per lane <= 16)
 
 template <int P>
 struct __align__(16) WarpTables {
   AxisTapB ys[2 * P];
-  AxisTapB xs[2 * P];
-  float4 xw[P];          // folded weights of the bin's columns xoff, xoff + sw, ... (<= 4 columns)
-  uint32_t xoff[P + 2];  // byte offset of the bin's first column
-  int xfirst[P + 2];     // its column index (backward: how far the accumulator window slides between bins)
+  AxisTapB xs[2 * kPadBins];
+  float4 xw[kPadBins];      // folded weights of the bin's columns xoff, xoff + sw, ... (<= 4 columns)
+  uint32_t xoff[kPadBins];  // byte offset of the bin's first column
+  int xfirst[kPadBins];     // its column index (backward: how far the accumulator window slides between bins)
   uint32_t ymode[2 * P];
   int lo[2][2 * P];      // scratch: neighbour indices per axis (lo = -1: sample contributes nothing)
   int hi[2][2 * P];
@@ -404,8 +404,10 @@ struct __align__(16) WarpTables {
 
 // Builds the tables of the warp's current RoI; returns the widest bin run in columns (0..4 -> bin
 // path with NB = max(3, run); > 4 -> per-sample path).  All 32 lanes must call.
+// Bins P .. nbins-1 are padding for lanes whose bin group is short (7 bins over two half-warps = 4 + 3): they alias
+// the last real bin's columns with zero weights.
 template <int P>
-__device__ __forceinline__ int build_tables_warp(WarpTables<P>& tb, const RoiGeom& g, const LvParam& lv, int lane) {
+__device__ __forceinline__ int build_tables_warp(WarpTables<P>& tb, const RoiGeom& g, const LvParam& lv, int lane, int nbins) {
   static_assert(2 * P <= 32 && P < 31, "one lane per sample");
   __syncwarp();  // the previous item's readers are done with the tables
   if (lane < 2 * P) {
@@ -463,6 +465,14 @@ __device__ __forceinline__ int build_tables_warp(WarpTables<P>& tb, const RoiGeo
   }
   run = __reduce_max_sync(0xffffffffu, run);
   __syncwarp();
+  if (lane >= P && lane < nbins) {
+    tb.xw[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    tb.xoff[lane] = tb.xoff[P - 1];
+    tb.xfirst[lane] = tb.xfirst[P - 1];
+    tb.xs[2 * lane] = AxisTapB{0u, 0u, 0.f, 0.f};
+    tb.xs[2 * lane + 1] = AxisTapB{0u, 0u, 0.f, 0.f};
+  }
+  __syncwarp();
   return run;
 }
 
@@ -470,20 +480,20 @@ __device__ __forceinline__ float2 ldg_f2b(const char* p) { return __ldg(reinterp
 
 // One window row -> T[0..6] = this lane's 7 x-bins (bins xb0 .. xb0+6), x-pooled.
 // CSW: compile-time column stride in elements (0 = use swb).
-template <int P, int NB, int CSW>
-__device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, int xb0, const uint32_t (&xo)[kXB],
-                                              const char* __restrict__ row, uint32_t swb, float2 (&T)[kXB]) {
+template <int P, int XB, int NB, int CSW>
+__device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, int xb0, const uint32_t (&xo)[XB],
+                                              const char* __restrict__ row, uint32_t swb, float2 (&T)[XB]) {
   const uint32_t cs = CSW ? (uint32_t)CSW * 4u : swb;
   if (NB > 0) {
-    float2 v[kXB][NB > 0 ? NB : 1];
+    float2 v[XB][NB > 0 ? NB : 1];
 #pragma unroll
-    for (int pw = 0; pw < kXB; ++pw) {
+    for (int pw = 0; pw < XB; ++pw) {
       const char* p = row + xo[pw];
 #pragma unroll
       for (int j = 0; j < NB; ++j) v[pw][j] = ldg_f2b(p + j * cs);
     }
 #pragma unroll
-    for (int pw = 0; pw < kXB; ++pw) {
+    for (int pw = 0; pw < XB; ++pw) {
       const float4 w = tb.xw[xb0 + pw];
       float2 t = __fmul2_rn(splat(w.x), v[pw][0]);
       t = ffma2(splat(w.y), v[pw][1], t);
@@ -492,17 +502,17 @@ __device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, int xb0, 
       T[pw] = t;
     }
   } else {
-    float2 a[2 * kXB], b[2 * kXB];
+    float2 a[2 * XB], b[2 * XB];
 #pragma unroll
-    for (int t = 0; t < 2 * kXB; ++t) {
+    for (int t = 0; t < 2 * XB; ++t) {
       const AxisTapB s = tb.xs[2 * xb0 + t];  // samples that contribute nothing have offsets 0 and weights 0
       a[t] = ldg_f2b(row + s.off_lo);
       b[t] = ldg_f2b(row + s.off_hi);
     }
 #pragma unroll
-    for (int pw = 0; pw < kXB; ++pw) T[pw] = make_float2(0.f, 0.f);
+    for (int pw = 0; pw < XB; ++pw) T[pw] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int t = 0; t < 2 * kXB; ++t) {
+    for (int t = 0; t < 2 * XB; ++t) {
       const AxisTapB s = tb.xs[2 * xb0 + t];
       if (s.w_lo + s.w_hi != 0.f) {  // uniform per half-warp
         T[t >> 1] = ffma2(splat(s.w_lo), a[t], T[t >> 1]);
@@ -514,15 +524,15 @@ __device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, int xb0, 
 
 // Walks the distinct rows of the window and writes this lane's two channels x 7 x-bins of the tile.
 // Every branch is warp-uniform and says so through a vote, so that ptxas keeps the uniform datapath.
-template <int P, int NB, int CSW>
+template <int P, int XB, int NB, int CSW>
 __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, int xb0, const char* __restrict__ fb, uint32_t swb,
                                               float* __restrict__ my) {
   constexpr int PP = P * P;
   constexpr uint32_t kAll = 0xffffffffu;
-  float2 T0[kXB], T1[kXB], acc[kXB];
-  uint32_t xo[kXB];  // bin column offsets stay in registers for the whole RoI
+  float2 T0[XB], T1[XB], acc[XB];
+  uint32_t xo[XB];  // bin column offsets stay in registers for the whole RoI
 #pragma unroll
-  for (int pw = 0; pw < kXB; ++pw) {
+  for (int pw = 0; pw < XB; ++pw) {
     T0[pw] = T1[pw] = acc[pw] = make_float2(0.f, 0.f);
     xo[pw] = NB > 0 ? tb.xoff[xb0 + pw] : 0u;
   }
@@ -532,6 +542,7 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, int xb0, 
   const bool lower = P != 7 || (threadIdx.x & 16) == 0;
   float* const o_a = my + (lower ? 0 : PP);
   float* const o_b = my + (lower ? PP : 0);
+  const int nmine = min(XB, P - xb0);  // real bins of this lane (the rest are padding)
 #pragma unroll 1
   for (int t = 0; t < 2 * P; ++t) {
     const uint32_t m = tb.ymode[t];
@@ -540,20 +551,20 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, int xb0, 
       const AxisTapB s = tb.ys[t];
       if (__any_sync(kAll, mode == kShift)) {
 #pragma unroll
-        for (int pw = 0; pw < kXB; ++pw) T0[pw] = T1[pw];
+        for (int pw = 0; pw < XB; ++pw) T0[pw] = T1[pw];
       } else if (__any_sync(kAll, mode == kNew)) {
-        pool_row_warp<P, NB, CSW>(tb, xb0, xo, fb + s.off_lo, swb, T0);
+        pool_row_warp<P, XB, NB, CSW>(tb, xb0, xo, fb + s.off_lo, swb, T0);
       }
       if (__any_sync(kAll, mode != kSame)) {
         if (__any_sync(kAll, m & kBorder)) {
 #pragma unroll
-          for (int pw = 0; pw < kXB; ++pw) T1[pw] = T0[pw];
+          for (int pw = 0; pw < XB; ++pw) T1[pw] = T0[pw];
         } else {
-          pool_row_warp<P, NB, CSW>(tb, xb0, xo, fb + s.off_hi, swb, T1);
+          pool_row_warp<P, XB, NB, CSW>(tb, xb0, xo, fb + s.off_hi, swb, T1);
         }
       }
 #pragma unroll
-      for (int pw = 0; pw < kXB; ++pw) {
+      for (int pw = 0; pw < XB; ++pw) {
         acc[pw] = ffma2(splat(s.w_lo), T0[pw], acc[pw]);
         acc[pw] = ffma2(splat(s.w_hi), T1[pw], acc[pw]);
       }
@@ -561,10 +572,12 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, int xb0, 
     if (t & 1) {  // bin row complete; count = 4 for sampling_ratio 2: multiply by 0.25 is exact
       const int o = (t >> 1) * P;
 #pragma unroll
-      for (int pw = 0; pw < kXB; ++pw) {
+      for (int pw = 0; pw < XB; ++pw) {
         const float e = acc[pw].x * 0.25f, f = acc[pw].y * 0.25f;
-        o_a[o + pw] = lower ? e : f;
-        o_b[o + pw] = lower ? f : e;
+        if (pw < nmine) {
+          o_a[o + pw] = lower ? e : f;
+          o_b[o + pw] = lower ? f : e;
+        }
         acc[pw] = make_float2(0.f, 0.f);
       }
     }
@@ -582,26 +595,26 @@ __device__ __forceinline__ void bulk_store_smem_to_global_hint(void* gdst, const
                : "memory");
 }
 
-template <int P>
+template <int P, int XB>
 struct WarpItem {
-  static constexpr int kHalves = P / kXB;                 // 1 (P = 7) or 2 (P = 14): x-bin groups per warp
+  static constexpr int kHalves = (P + XB - 1) / XB;       // x-bin groups per warp: 1 (P=7, XB=7) or 2 (P=14 XB=7; P=7 XB=4)
   static constexpr int kPairs = 32 / kHalves;             // channel pairs per warp item
   static constexpr int kChannels = 2 * kPairs;            // 64 or 32
   static constexpr int kTileFloats = kChannels * P * P;   // 12 544 B or 25 088 B
 };
 
-template <int P, int WARPS, int CSW>
-__global__ void __launch_bounds__(WARPS * 32, P == 7 ? 4 : 2)
+template <int P, int XB, int WARPS, int CSW>
+__global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
     roi_fwd_warp_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out, int groups, int stream_out, int ipw) {
-  using WI = WarpItem<P>;
-  static_assert(P % kXB == 0 && WI::kHalves <= 2, "P must be 7 or 14");
+  using WI = WarpItem<P, XB>;
+  static_assert(WI::kHalves <= 2 && WI::kHalves * XB <= kPadBins, "x-bins: one or two groups per warp");
   constexpr int PP = P * P;
   constexpr uint32_t kAll = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = __shfl_sync(kAll, (int)(threadIdx.x >> 5), 0);  // tells ptxas the value is warp-uniform
   const int lane = threadIdx.x & 31;
   const int pair = lane % WI::kPairs;          // channel pair of this lane inside the item
-  const int xb0 = (lane / WI::kPairs) * kXB;   // first x-bin of this lane
+  const int xb0 = (lane / WI::kPairs) * XB;   // first x-bin of this lane
   float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * WI::kTileFloats;
   WarpTables<P>& tb = reinterpret_cast<WarpTables<P>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats)[warp];
   float* my = tile + (size_t)(2 * pair) * PP + xb0;
@@ -625,7 +638,7 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? 4 : 2)
     const bool live = __any_sync(kAll, g.live);
     const LvParam& lv = p.lv[live ? g.lvl : 0];
     int run = 0;
-    if (live) run = build_tables_warp<P>(tb, g, lv, lane);
+    if (live) run = build_tables_warp<P>(tb, g, lv, lane, WI::kHalves * XB);
     // the previous item's bulk store must have finished READING the tile before it is rewritten
     if (lane == 0) bulk_wait_read_all();
     __syncwarp();
@@ -635,9 +648,9 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? 4 : 2)
       // lanes past the last channel pair of a short group redo the last pair (their tile rows are not stored)
       const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)g.b * lv.sn + c0 + min(2 * pair, nch - 2));  // sc == 1
       const uint32_t swb = (uint32_t)lv.sw * 4u;
-      if (__all_sync(kAll, run <= 3)) roi_warp_body<P, 3, CSW>(tb, xb0, fb, swb, my);
-      else if (__all_sync(kAll, run == 4)) roi_warp_body<P, 4, CSW>(tb, xb0, fb, swb, my);
-      else roi_warp_body<P, 0, CSW>(tb, xb0, fb, swb, my);
+      if (__all_sync(kAll, run <= 3)) roi_warp_body<P, XB, 3, CSW>(tb, xb0, fb, swb, my);
+      else if (__all_sync(kAll, run == 4)) roi_warp_body<P, XB, 4, CSW>(tb, xb0, fb, swb, my);
+      else roi_warp_body<P, XB, 0, CSW>(tb, xb0, fb, swb, my);
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -828,9 +841,9 @@ __device__ __forceinline__ void red_add_f2(char* p, float2 v, bool active) {
   if (active) atomicAdd(reinterpret_cast<float2*>(p), v);
 }
 
-template <int P, int NB, int CSW>
-__device__ __forceinline__ void scatter_row_warp(const WarpTables<P>& tb, int xb0, const uint32_t (&xo)[kXB], const int (&xstep)[kXB],
-                                                 char* __restrict__ row, uint32_t swb, const float2 (&U)[kXB], bool active) {
+template <int P, int XB, int NB, int CSW>
+__device__ __forceinline__ void scatter_row_warp(const WarpTables<P>& tb, int xb0, const uint32_t (&xo)[XB], const int (&xstep)[XB],
+                                                 char* __restrict__ row, uint32_t swb, const float2 (&U)[XB], bool active) {
   const uint32_t cs = CSW ? (uint32_t)CSW * 4u : swb;
   if (NB > 0) {
     float2 A[NB > 0 ? NB : 1];
@@ -838,7 +851,7 @@ __device__ __forceinline__ void scatter_row_warp(const WarpTables<P>& tb, int xb
     for (int j = 0; j < NB; ++j) A[j] = make_float2(0.f, 0.f);
     uint32_t base = xo[0];
 #pragma unroll
-    for (int pw = 0; pw < kXB; ++pw) {
+    for (int pw = 0; pw < XB; ++pw) {
       if (pw > 0) {
         const int d = min(xstep[pw], NB);  // columns the window slides (uniform per half-warp)
 #pragma unroll 1
@@ -860,7 +873,7 @@ __device__ __forceinline__ void scatter_row_warp(const WarpTables<P>& tb, int xb
     for (int j = 0; j < NB; ++j) red_add_f2(row + base + j * cs, A[j], active);
   } else {
 #pragma unroll
-    for (int t = 0; t < 2 * kXB; ++t) {
+    for (int t = 0; t < 2 * XB; ++t) {
       const AxisTapB s = tb.xs[2 * xb0 + t];
       if (s.w_lo + s.w_hi != 0.f) {  // uniform per half-warp
         red_add_f2(row + s.off_lo, make_float2(s.w_lo * U[t >> 1].x, s.w_lo * U[t >> 1].y), active);
@@ -870,16 +883,16 @@ __device__ __forceinline__ void scatter_row_warp(const WarpTables<P>& tb, int xb
   }
 }
 
-template <int P, int NB, int CSW>
+template <int P, int XB, int NB, int CSW>
 __device__ __forceinline__ void roi_warp_body_bwd(const WarpTables<P>& tb, int xb0, char* __restrict__ fb, uint32_t swb,
                                                   const float* __restrict__ my, bool active) {
   constexpr int PP = P * P;
   constexpr uint32_t kAll = 0xffffffffu;
-  float2 U0[kXB], U1[kXB], gq[kXB];
-  uint32_t xo[kXB];
-  int xstep[kXB];
+  float2 U0[XB], U1[XB], gq[XB];
+  uint32_t xo[XB];
+  int xstep[XB];
 #pragma unroll
-  for (int pw = 0; pw < kXB; ++pw) {
+  for (int pw = 0; pw < XB; ++pw) {
     U0[pw] = U1[pw] = gq[pw] = make_float2(0.f, 0.f);
     xo[pw] = NB > 0 ? tb.xoff[xb0 + pw] : 0u;
     xstep[pw] = (NB > 0 && pw > 0) ? tb.xfirst[xb0 + pw] - tb.xfirst[xb0 + pw - 1] : 0;
@@ -888,6 +901,7 @@ __device__ __forceinline__ void roi_warp_body_bwd(const WarpTables<P>& tb, int x
   const bool lower = P != 7 || (threadIdx.x & 16) == 0;
   const float* const i_a = my + (lower ? 0 : PP);
   const float* const i_b = my + (lower ? PP : 0);
+  const int nmine = min(XB, P - xb0);
   uint32_t r0 = 0xffffffffu, r1 = 0xffffffffu;  // byte offsets of the two cached rows (all-ones: empty)
 #pragma unroll 1
   for (int t = 0; t <= 2 * P; ++t) {  // the extra iteration flushes both rows
@@ -895,8 +909,8 @@ __device__ __forceinline__ void roi_warp_body_bwd(const WarpTables<P>& tb, int x
     if (!(t & 1) && t < 2 * P) {  // entering bin row t/2: grad_out[ph][:] / count (count = 4, exact)
       const int o = (t >> 1) * P;
 #pragma unroll
-      for (int pw = 0; pw < kXB; ++pw) {
-        const float e = i_a[o + pw] * 0.25f, f = i_b[o + pw] * 0.25f;
+      for (int pw = 0; pw < XB; ++pw) {
+        const float e = pw < nmine ? i_a[o + pw] * 0.25f : 0.f, f = pw < nmine ? i_b[o + pw] * 0.25f : 0.f;
         gq[pw] = lower ? make_float2(e, f) : make_float2(f, e);
       }
     }
@@ -905,9 +919,9 @@ __device__ __forceinline__ void roi_warp_body_bwd(const WarpTables<P>& tb, int x
       const int nflush = __any_sync(kAll, mode == kShift) ? 1 : (__any_sync(kAll, mode == kNew) ? 2 : 0);
 #pragma unroll 1
       for (int f = 0; f < nflush; ++f) {  // the single scatter site
-        if (__any_sync(kAll, r0 != 0xffffffffu)) scatter_row_warp<P, NB, CSW>(tb, xb0, xo, xstep, fb + r0, swb, U0, active);
+        if (__any_sync(kAll, r0 != 0xffffffffu)) scatter_row_warp<P, XB, NB, CSW>(tb, xb0, xo, xstep, fb + r0, swb, U0, active);
 #pragma unroll
-        for (int pw = 0; pw < kXB; ++pw) {
+        for (int pw = 0; pw < XB; ++pw) {
           U0[pw] = U1[pw];
           U1[pw] = make_float2(0.f, 0.f);
         }
@@ -919,14 +933,14 @@ __device__ __forceinline__ void roi_warp_body_bwd(const WarpTables<P>& tb, int x
         r0 = s.off_lo;
         if (__any_sync(kAll, m & kBorder)) {
 #pragma unroll
-          for (int pw = 0; pw < kXB; ++pw) {
+          for (int pw = 0; pw < XB; ++pw) {
             U0[pw] = ffma2(splat(s.w_lo), gq[pw], U0[pw]);
             U0[pw] = ffma2(splat(s.w_hi), gq[pw], U0[pw]);
           }
         } else {
           r1 = s.off_hi;
 #pragma unroll
-          for (int pw = 0; pw < kXB; ++pw) {
+          for (int pw = 0; pw < XB; ++pw) {
             U0[pw] = ffma2(splat(s.w_lo), gq[pw], U0[pw]);
             U1[pw] = ffma2(splat(s.w_hi), gq[pw], U1[pw]);
           }
@@ -936,17 +950,17 @@ __device__ __forceinline__ void roi_warp_body_bwd(const WarpTables<P>& tb, int x
   }
 }
 
-template <int P, int WARPS, int CSW>
-__global__ void __launch_bounds__(WARPS * 32, P == 7 ? 4 : 2)
+template <int P, int XB, int WARPS, int CSW>
+__global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
     roi_bwd_warp_kernel(const __grid_constant__ RoiParams p, const float* __restrict__ gout, int groups, int ipw) {
-  using WI = WarpItem<P>;
+  using WI = WarpItem<P, XB>;
   constexpr int PP = P * P;
   constexpr uint32_t kAll = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = __shfl_sync(kAll, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int pair = lane % WI::kPairs;
-  const int xb0 = (lane / WI::kPairs) * kXB;
+  const int xb0 = (lane / WI::kPairs) * XB;
   float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * WI::kTileFloats;
   WarpTables<P>& tb = reinterpret_cast<WarpTables<P>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats)[warp];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<P>)) + warp;
@@ -976,7 +990,7 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? 4 : 2)
       mbar_expect_tx(bar, bytes);
       bulk_load_global_to_smem(tile, gout + ((size_t)k * p.C + c0) * PP, bytes, bar);
     }
-    const int run = build_tables_warp<P>(tb, g, lv, lane);
+    const int run = build_tables_warp<P>(tb, g, lv, lane, WI::kHalves * XB);
     bool mono = true;  // the sliding window needs non-decreasing bin starts (always true for x2 >= x1)
     if (lane > 0 && lane < P) mono = tb.xfirst[lane] >= tb.xfirst[lane - 1];
     mono = __all_sync(kAll, mono);
@@ -986,9 +1000,9 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? 4 : 2)
     const bool active = 2 * pair < nch;
     char* fb = reinterpret_cast<char*>(lv.data + (size_t)g.b * lv.sn + c0 + min(2 * pair, nch - 2));
     const uint32_t swb = (uint32_t)lv.sw * 4u;
-    if (mono && run <= 3) roi_warp_body_bwd<P, 3, CSW>(tb, xb0, fb, swb, my, active);
-    else if (mono && run == 4) roi_warp_body_bwd<P, 4, CSW>(tb, xb0, fb, swb, my, active);
-    else roi_warp_body_bwd<P, 0, CSW>(tb, xb0, fb, swb, my, active);
+    if (mono && run <= 3) roi_warp_body_bwd<P, XB, 3, CSW>(tb, xb0, fb, swb, my, active);
+    else if (mono && run == 4) roi_warp_body_bwd<P, XB, 4, CSW>(tb, xb0, fb, swb, my, active);
+    else roi_warp_body_bwd<P, XB, 0, CSW>(tb, xb0, fb, swb, my, active);
   }
 }
 
@@ -1069,9 +1083,9 @@ static bool env_is(const char* name, const char* value) {
   return v && strcmp(v, value) == 0;
 }
 
-template <int P, int CSW>
+template <int P, int XB, int CSW>
 static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
-  using WI = WarpItem<P>;
+  using WI = WarpItem<P, XB>;
   constexpr int WARPS = 4;
   const int groups = (p.C + WI::kChannels - 1) / WI::kChannels;
   const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<P>);
@@ -1088,7 +1102,7 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
   }
   LCR_REQUIRE(want < (1ll << 31), LCR_ERR_CAPACITY);
   const int blocks = (int)want;
-  auto kern = roi_fwd_warp_kernel<P, WARPS, CSW>;
+  auto kern = roi_fwd_warp_kernel<P, XB, WARPS, CSW>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1101,9 +1115,9 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
   return after_launch();
 }
 
-template <int P, int CSW>
+template <int P, int XB, int CSW>
 static int launch_bwd_warp(const RoiParams& p, const float* gout, cudaStream_t st) {
-  using WI = WarpItem<P>;
+  using WI = WarpItem<P, XB>;
   constexpr int WARPS = 4;
   const int groups = (p.C + WI::kChannels - 1) / WI::kChannels;
   const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<P>) + WARPS * 8;
@@ -1111,7 +1125,7 @@ static int launch_bwd_warp(const RoiParams& p, const float* gout, cudaStream_t s
   const int ipw = items >= (long long)WARPS * 2 * 4 * sm_count() ? 2 : 1;
   const long long want = (items + (long long)WARPS * ipw - 1) / ((long long)WARPS * ipw);
   LCR_REQUIRE(want < (1ll << 31), LCR_ERR_CAPACITY);
-  auto kern = roi_bwd_warp_kernel<P, WARPS, CSW>;
+  auto kern = roi_bwd_warp_kernel<P, XB, WARPS, CSW>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1151,8 +1165,11 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
   cudaStream_t st = as_stream(stream);
   if (fast_eligible(p, out)) {
     if (warp_eligible(p) && !env_is("LCR_ROI_FWD", "cta")) {
-      if (PH == 7) return all_sw_equal(p, 256) ? launch_fwd_warp<7, 256>(p, out, st) : launch_fwd_warp<7, 0>(p, out, st);
-      return all_sw_equal(p, 256) ? launch_fwd_warp<14, 256>(p, out, st) : launch_fwd_warp<14, 0>(p, out, st);
+      // P = 7: LCR_ROI_SPLIT=1 selects the 32-channel items (half-warps take x-bins 0-3 / 4-6: 6 CTAs/SM instead of 4)
+      const bool split = env_is("LCR_ROI_SPLIT", "1");
+      if (PH == 7 && split) return all_sw_equal(p, 256) ? launch_fwd_warp<7, 4, 256>(p, out, st) : launch_fwd_warp<7, 4, 0>(p, out, st);
+      if (PH == 7) return all_sw_equal(p, 256) ? launch_fwd_warp<7, 7, 256>(p, out, st) : launch_fwd_warp<7, 7, 0>(p, out, st);
+      return all_sw_equal(p, 256) ? launch_fwd_warp<14, 7, 256>(p, out, st) : launch_fwd_warp<14, 7, 0>(p, out, st);
     }
     if (PH == 7) return launch_fast<7, 128, false>(p, out, st);
     return launch_fast<14, 32, false>(p, out, st);
@@ -1183,8 +1200,10 @@ extern "C" int lcr_roi_align_bwd_f32(const float* grad_out, const LcrFeatLevel* 
   LCR_REQUIRE(grad_out, LCR_ERR_INVALID_ARG);
   if (fast_eligible(p, grad_out)) {
     if (warp_eligible(p) && !env_is("LCR_ROI_BWD", "cta")) {
-      if (PH == 7) return all_sw_equal(p, 256) ? launch_bwd_warp<7, 256>(p, grad_out, st) : launch_bwd_warp<7, 0>(p, grad_out, st);
-      return all_sw_equal(p, 256) ? launch_bwd_warp<14, 256>(p, grad_out, st) : launch_bwd_warp<14, 0>(p, grad_out, st);
+      const bool split = env_is("LCR_ROI_SPLIT", "1");
+      if (PH == 7 && split) return all_sw_equal(p, 256) ? launch_bwd_warp<7, 4, 256>(p, grad_out, st) : launch_bwd_warp<7, 4, 0>(p, grad_out, st);
+      if (PH == 7) return all_sw_equal(p, 256) ? launch_bwd_warp<7, 7, 256>(p, grad_out, st) : launch_bwd_warp<7, 7, 0>(p, grad_out, st);
+      return all_sw_equal(p, 256) ? launch_bwd_warp<14, 7, 256>(p, grad_out, st) : launch_bwd_warp<14, 7, 0>(p, grad_out, st);
     }
     if (PH == 7) return launch_fast<7, 128, true>(p, const_cast<float*>(grad_out), st);
     return launch_fast<14, 32, true>(p, const_cast<float*>(grad_out), st);

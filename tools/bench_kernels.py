@@ -68,7 +68,7 @@ def main():
         print(json.dumps(kw), flush=True)
 
     def setenv(env):
-        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT"):
+        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB"):
             os.environ.pop(k, None)
         os.environ.update(env)
 
@@ -76,7 +76,8 @@ def main():
         bytes_roi = 4 * n_props * B.C * 49 + F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS
         ref = None
         for name, env in [("cta(r01)", {"LCR_ROI_FWD": "cta"}), ("warp,persistent", {"LCR_ROI_IPW": "0"}), ("warp,ipw1", {"LCR_ROI_IPW": "1"}),
-                          ("warp,ipw2", {"LCR_ROI_IPW": "2"}), ("warp,ipw3", {"LCR_ROI_IPW": "3"})]:
+                          ("warp,ipw2", {"LCR_ROI_IPW": "2"}), ("warp,split32ch", {"LCR_ROI_SPLIT": "1"}),
+                          ("warp,split32ch,ipw4", {"LCR_ROI_SPLIT": "1", "LCR_ROI_IPW": "4"})]:
             setenv(env)
             out = pipe.pool(feat, props.rois)
             torch.cuda.synchronize()
@@ -97,7 +98,7 @@ def main():
         gin = torch.empty((F, B.C, B.FH, B.FW), device=dev).contiguous(memory_format=torch.channels_last)
         bytes_bwd = 4 * n_props * B.C * 49 + 3 * F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS
         ref = None
-        for name, env in [("cta(r01)", {"LCR_ROI_BWD": "cta"}), ("warp", {})]:
+        for name, env in [("cta(r01)", {"LCR_ROI_BWD": "cta"}), ("warp", {}), ("warp,split32ch", {"LCR_ROI_SPLIT": "1"})]:
             setenv(env)
             ops.roi_align_bwd(gout, [gin], [0.25], props.rois, None, 2, False, zero_grad=True)
             torch.cuda.synchronize()
@@ -118,7 +119,8 @@ def main():
         boxes_flat = det.boxes.reshape(-1, 4)
         bytes_paste = n_det * (B.IMG_H * B.IMG_W + B.M * B.M * 4 + 16)
         ref = None
-        for name, env in [("rows16(r01)", {"LCR_PASTE": "rows16"}), ("bulk", {})]:
+        for name, env in [("rows16(r01)", {"LCR_PASTE": "rows16"}), ("bulk", {}), ("bulk,zb8", {"LCR_PASTE_ZB_KB": "8"}),
+                          ("bulk,zb32", {"LCR_PASTE_ZB_KB": "32"}), ("bulk,zb64", {"LCR_PASTE_ZB_KB": "64"})]:
             setenv(env)
             masks.fill_(7)
             ops.paste_masks(probs_d, boxes_flat, B.IMG_H, B.IMG_W, 0.5, 255, valid=det.valid, out=masks)
@@ -133,6 +135,9 @@ def main():
             emit(kernel="paste", variant=name, ms=med, ms_min=mn, GBps=bytes_paste / 1e9 / (med * 1e-3),
                  frac=bytes_paste / 1e9 / (med * 1e-3) / peak, identical_to_first=same, detections=n_det)
         setenv({})
+        med, mn = timed(lambda: masks.zero_(), args.reps)
+        emit(kernel="reference: torch zero_() of the same 11.7 GB (pure HBM write stream)", ms=med, ms_min=mn,
+             GBps=masks.numel() / 1e9 / (med * 1e-3), frac=masks.numel() / 1e9 / (med * 1e-3) / peak)
         del masks
 
     if "select" in only:

@@ -227,6 +227,8 @@ constexpr int kPreEPT = 8;
 constexpr int kSortThreads = 1024;
 
 __global__ void __launch_bounds__(kPreThreads) rpn_prefilter_kernel(const __grid_constant__ SelParams p, float band_lo, float band_hi) {
+  __shared__ uint32_t s_warp[kPreThreads / 32];
+  __shared__ uint32_t s_base;
   const int seg = blockIdx.y;
   const int b = seg / p.L, l = seg - b * p.L;
   const SelLevel& lv = p.lv[l];
@@ -241,6 +243,8 @@ __global__ void __launch_bounds__(kPreThreads) rpn_prefilter_kernel(const __grid
     const int m = m0 + j * kPreThreads;
     v[j] = m < n ? __ldg(obj + m) : -INFINITY;   // -inf never passes and is not NaN
   }
+  uint32_t bits = 0u;   // bit j: element j of this thread survives the threshold
+  bool any_nan = false;
 #pragma unroll
   for (int j = 0; j < kPreEPT; ++j) {
     const int m = m0 + j * kPreThreads;
@@ -250,22 +254,43 @@ __global__ void __launch_bounds__(kPreThreads) rpn_prefilter_kernel(const __grid
       const float s = sigmoid_f32(x);
       pass = p.score_strict ? (s > p.score_thresh) : (s >= p.score_thresh);
     }
-    const bool isnan_ = (x != x);
-    const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass);
-    const unsigned nm = __ballot_sync(0xFFFFFFFFu, isnan_);
-    if (nm && lane_id() == 0) atomicAdd(&p.pre_count[2 * seg + 1], (uint32_t)__popc(nm));
-    if (pm) {
-      uint32_t pos0 = 0;
-      if (lane_id() == 0) pos0 = atomicAdd(&p.pre_count[2 * seg], (uint32_t)__popc(pm));
-      pos0 = __shfl_sync(0xFFFFFFFFu, pos0, 0);
-      if (pass) {
-        const uint32_t pos = pos0 + __popc(pm & ((1u << lane_id()) - 1u));
-        if (pos < (uint32_t)kPreCap) {
-          const int a = m / P, pp = m - a * P;
-          const uint32_t flat = (uint32_t)(pp * A + a);
-          cand[pos] = ((unsigned long long)make_key(x, p.topk_on_sigmoid) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
-        }
+    bits |= pass ? (1u << j) : 0u;
+    any_nan |= (x != x);
+  }
+  // ONE atomic per CTA (2048 logits): same-address atomics with a return value serialise at L2, and a per-warp
+  // append made them the whole cost of this kernel (ncu r01c: 67 % of the stall samples on the broadcast after it).
+  const uint32_t cnt = __popc(bits);
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  const unsigned nm = __ballot_sync(0xFFFFFFFFu, any_nan);
+  if (nm && lane == 0) atomicAdd(&p.pre_count[2 * seg + 1], (uint32_t)__popc(nm));   // rare: sends the segment to the general kernel
+  __syncthreads();
+  uint32_t woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kPreThreads / 32; ++w) {
+    const uint32_t t = s_warp[w];
+    if (w < warp) woff += t;
+    total += t;
+  }
+  if (threadIdx.x == 0) s_base = total ? atomicAdd(&p.pre_count[2 * seg], total) : 0u;
+  __syncthreads();
+  uint32_t pos = s_base + woff + incl - cnt;
+#pragma unroll
+  for (int j = 0; j < kPreEPT; ++j) {
+    if ((bits >> j) & 1u) {
+      if (pos < (uint32_t)kPreCap) {
+        const int m = m0 + j * kPreThreads;
+        const int a = m / P, pp = m - a * P;
+        const uint32_t flat = (uint32_t)(pp * A + a);
+        cand[pos] = ((unsigned long long)make_key(v[j], p.topk_on_sigmoid) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
       }
+      ++pos;
     }
   }
 }

@@ -605,7 +605,7 @@ struct WarpItem {
 
 template <int P, int XB, int WARPS, int CSW>
 __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
-    roi_fwd_warp_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out, int groups, int stream_out, int ipw) {
+    roi_fwd_warp_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out, int groups, int flags, int ipw) {
   using WI = WarpItem<P, XB>;
   static_assert(WI::kHalves <= 2 && WI::kHalves * XB <= kPadBins, "x-bins: one or two groups per warp");
   constexpr int PP = P * P;
@@ -616,29 +616,66 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
   const int pair = lane % WI::kPairs;          // channel pair of this lane inside the item
   const int xb0 = (lane / WI::kPairs) * XB;   // first x-bin of this lane
   float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * WI::kTileFloats;
-  WarpTables<P>& tb = reinterpret_cast<WarpTables<P>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats)[warp];
+  WarpTables<P>* tbs = reinterpret_cast<WarpTables<P>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats);
+  __shared__ int s_run[WARPS], s_b[WARPS], s_lvl[WARPS];
   float* my = tile + (size_t)(2 * pair) * PP + xb0;
   const uint64_t pol = l2_policy_evict_first();
   const long long items = (long long)p.K * groups;
-  // Work order.  ipw > 0: CTA b owns the WARPS*ipw consecutive items starting at b*WARPS*ipw (warp w takes
-  // every WARPS-th of them); the grid covers all items and the hardware launches CTAs in index order as SMs
-  // drain, so the RoIs in flight are always neighbours in the list (one or two frames: their feature maps
-  // stay L2-resident).  ipw == 0: persistent grid with a static stride (kept for A/B runs; warps drift
-  // apart by many frames and the maps are re-read from HBM).
+  // Work order.  ipw > 0: CTA b owns the WARPS*ipw consecutive items starting at b*WARPS*ipw; the grid covers all
+  // items and the hardware launches CTAs in index order as SMs drain, so the RoIs in flight are always neighbours
+  // in the list (one or two frames: their feature maps stay L2-resident).  ipw == 0: persistent grid with a static
+  // stride (kept for A/B runs; warps drift apart by many frames and the maps are re-read from HBM).
+  //
+  // Shared tables: when a RoI has exactly WARPS channel groups (C = 256), the CTA's ipw RoIs are shared by its warps
+  // (warp w = channel group w), so the geometry / tap / fold tables are built ONCE per RoI (warp i builds RoI i) behind
+  // the kernel's only __syncthreads instead of once per warp item (17 % of the executed instructions, ncu r01c).
+  const bool shared_tables = groups == WARPS && ipw >= 1 && ipw <= WARPS && !(flags & 2);
+  const int k0 = blockIdx.x * ipw;
+  if (shared_tables) {
+    if (warp < ipw && k0 + warp < p.K) {
+      const RoiGeom g = roi_geom(p, k0 + warp);
+      const bool live = __any_sync(kAll, g.live);
+      int run = -1;
+      if (live) run = build_tables_warp<P>(tbs[warp], g, p.lv[g.lvl], lane, WI::kHalves * XB);
+      if (lane == 0) {
+        s_run[warp] = run;
+        s_b[warp] = g.b;
+        s_lvl[warp] = live ? g.lvl : 0;
+      }
+    }
+    __syncthreads();
+  }
   const long long first = ipw > 0 ? (long long)blockIdx.x * WARPS * ipw + warp : (long long)blockIdx.x * WARPS + warp;
   const long long last = ipw > 0 ? min(items, ((long long)blockIdx.x + 1) * WARPS * ipw) : items;
   const long long stride = ipw > 0 ? WARPS : (long long)gridDim.x * WARPS;
 
   for (long long item = first; item < last; item += stride) {
-    const int k = (int)(item / groups);
-    const int cg = (int)(item - (long long)k * groups);
+    int k, cg, run = 0, gb, glvl;
+    bool live;
+    const WarpTables<P>* tbp;
+    if (shared_tables) {  // block-uniform
+      const int slot = (int)((item - first) / WARPS);
+      k = k0 + slot;
+      cg = warp;
+      run = s_run[slot];
+      live = __any_sync(kAll, run >= 0);
+      gb = s_b[slot];
+      glvl = s_lvl[slot];
+      tbp = &tbs[slot];
+    } else {
+      k = (int)(item / groups);
+      cg = (int)(item - (long long)k * groups);
+      const RoiGeom g = roi_geom(p, k);
+      live = __any_sync(kAll, g.live);
+      gb = g.b;
+      glvl = live ? g.lvl : 0;
+      if (live) run = build_tables_warp<P>(tbs[warp], g, p.lv[glvl], lane, WI::kHalves * XB);
+      tbp = &tbs[warp];
+    }
+    const WarpTables<P>& tb = *tbp;
     const int c0 = cg * WI::kChannels;
     const int nch = min(WI::kChannels, p.C - c0);  // multiple of 4
-    const RoiGeom g = roi_geom(p, k);
-    const bool live = __any_sync(kAll, g.live);
-    const LvParam& lv = p.lv[live ? g.lvl : 0];
-    int run = 0;
-    if (live) run = build_tables_warp<P>(tb, g, lv, lane, WI::kHalves * XB);
+    const LvParam& lv = p.lv[glvl];
     // the previous item's bulk store must have finished READING the tile before it is rewritten
     if (lane == 0) bulk_wait_read_all();
     __syncwarp();
@@ -646,7 +683,7 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
       for (int j = lane; j < WI::kTileFloats; j += 32) tile[j] = 0.f;
     } else {
       // lanes past the last channel pair of a short group redo the last pair (their tile rows are not stored)
-      const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)g.b * lv.sn + c0 + min(2 * pair, nch - 2));  // sc == 1
+      const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)gb * lv.sn + c0 + min(2 * pair, nch - 2));  // sc == 1
       const uint32_t swb = (uint32_t)lv.sw * 4u;
       if (__all_sync(kAll, run <= 3)) roi_warp_body<P, XB, 3, CSW>(tb, xb0, fb, swb, my);
       else if (__all_sync(kAll, run == 4)) roi_warp_body<P, XB, 4, CSW>(tb, xb0, fb, swb, my);
@@ -657,7 +694,7 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
     if (lane == 0) {
       float* dst = out + ((size_t)k * p.C + c0) * PP;
       const uint32_t bytes = (uint32_t)(nch * PP * sizeof(float));
-      if (stream_out) bulk_store_smem_to_global_hint(dst, tile, bytes, pol);
+      if (flags & 1) bulk_store_smem_to_global_hint(dst, tile, bytes, pol);
       else bulk_store_smem_to_global(dst, tile, bytes);
       bulk_commit();
     }
@@ -952,7 +989,7 @@ __device__ __forceinline__ void roi_warp_body_bwd(const WarpTables<P>& tb, int x
 
 template <int P, int XB, int WARPS, int CSW>
 __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
-    roi_bwd_warp_kernel(const __grid_constant__ RoiParams p, const float* __restrict__ gout, int groups, int ipw) {
+    roi_bwd_warp_kernel(const __grid_constant__ RoiParams p, const float* __restrict__ gout, int groups, int flags, int ipw) {
   using WI = WarpItem<P, XB>;
   constexpr int PP = P * P;
   constexpr uint32_t kAll = 0xffffffffu;
@@ -962,7 +999,6 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
   const int pair = lane % WI::kPairs;
   const int xb0 = (lane / WI::kPairs) * XB;
   float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * WI::kTileFloats;
-  WarpTables<P>& tb = reinterpret_cast<WarpTables<P>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats)[warp];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<P>)) + warp;
   const float* my = tile + (size_t)(2 * pair) * PP + xb0;
   if (lane == 0) {
@@ -974,15 +1010,62 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
   const long long items = (long long)p.K * groups;
   const long long first = (long long)blockIdx.x * WARPS * ipw + warp;
   const long long last = min(items, ((long long)blockIdx.x + 1) * WARPS * ipw);
+  // shared tables: as in the forward kernel (one table build per RoI when a RoI has exactly WARPS channel groups)
+  __shared__ int s_run[WARPS], s_b[WARPS], s_lvl[WARPS];
+  WarpTables<P>* tbs = reinterpret_cast<WarpTables<P>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats);
+  const bool shared_tables = groups == WARPS && ipw >= 1 && ipw <= WARPS && !(flags & 2);
+  const int k0 = blockIdx.x * ipw;
+  if (shared_tables) {
+    if (warp < ipw && k0 + warp < p.K) {
+      const RoiGeom g = roi_geom(p, k0 + warp);
+      const bool live = __any_sync(kAll, g.live);
+      int run = -1;
+      if (live) {
+        run = build_tables_warp<P>(tbs[warp], g, p.lv[g.lvl], lane, WI::kHalves * XB);
+        bool mono = true;  // the sliding window needs non-decreasing bin starts (always true for x2 >= x1)
+        if (lane > 0 && lane < P) mono = tbs[warp].xfirst[lane] >= tbs[warp].xfirst[lane - 1];
+        if (!__all_sync(kAll, mono)) run = 99;  // per-sample path
+      }
+      if (lane == 0) {
+        s_run[warp] = run;
+        s_b[warp] = g.b;
+        s_lvl[warp] = live ? g.lvl : 0;
+      }
+    }
+    __syncthreads();
+  }
 
   for (long long item = first; item < last; item += WARPS) {
-    const int k = (int)(item / groups);
-    const int cg = (int)(item - (long long)k * groups);
+    int k, cg, run, gb, glvl;
+    bool live;
+    const WarpTables<P>* tbp;
+    if (shared_tables) {  // block-uniform
+      const int slot = (int)((item - first) / WARPS);
+      k = k0 + slot;
+      cg = warp;
+      run = s_run[slot];
+      live = __any_sync(kAll, run >= 0);
+      gb = s_b[slot];
+      glvl = s_lvl[slot];
+      tbp = &tbs[slot];
+    } else {
+      k = (int)(item / groups);
+      cg = (int)(item - (long long)k * groups);
+      run = -1;
+      tbp = &tbs[warp];
+    }
+    RoiGeom g{};
+    if (!shared_tables) {
+      g = roi_geom(p, k);
+      live = __any_sync(kAll, g.live);
+      gb = g.b;
+      glvl = live ? g.lvl : 0;
+    }
+    if (!live) continue;  // warp-uniform
+    const WarpTables<P>& tb = *tbp;
     const int c0 = cg * WI::kChannels;
     const int nch = min(WI::kChannels, p.C - c0);
-    const RoiGeom g = roi_geom(p, k);
-    if (!__any_sync(kAll, g.live)) continue;  // warp-uniform
-    const LvParam& lv = p.lv[g.lvl];
+    const LvParam& lv = p.lv[glvl];
     fence_proxy_async_smem();  // generic-proxy reads of the old tile are ordered before the async-proxy refill
     __syncwarp();              // every lane is done with the previous tile
     if (lane == 0) {
@@ -990,18 +1073,20 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
       mbar_expect_tx(bar, bytes);
       bulk_load_global_to_smem(tile, gout + ((size_t)k * p.C + c0) * PP, bytes, bar);
     }
-    const int run = build_tables_warp<P>(tb, g, lv, lane, WI::kHalves * XB);
-    bool mono = true;  // the sliding window needs non-decreasing bin starts (always true for x2 >= x1)
-    if (lane > 0 && lane < P) mono = tb.xfirst[lane] >= tb.xfirst[lane - 1];
-    mono = __all_sync(kAll, mono);
+    if (!shared_tables) {  // per-warp tables, built while the tile is in flight
+      run = build_tables_warp<P>(tbs[warp], g, lv, lane, WI::kHalves * XB);
+      bool mono = true;
+      if (lane > 0 && lane < P) mono = tbs[warp].xfirst[lane] >= tbs[warp].xfirst[lane - 1];
+      if (!__all_sync(kAll, mono)) run = 99;
+    }
     mbar_wait(bar, parity);
     parity ^= 1u;
     // every lane runs the (vote-synchronised) walk; lanes past a short channel group only skip the atomics
     const bool active = 2 * pair < nch;
-    char* fb = reinterpret_cast<char*>(lv.data + (size_t)g.b * lv.sn + c0 + min(2 * pair, nch - 2));
+    char* fb = reinterpret_cast<char*>(lv.data + (size_t)gb * lv.sn + c0 + min(2 * pair, nch - 2));
     const uint32_t swb = (uint32_t)lv.sw * 4u;
-    if (mono && run <= 3) roi_warp_body_bwd<P, XB, 3, CSW>(tb, xb0, fb, swb, my, active);
-    else if (mono && run == 4) roi_warp_body_bwd<P, XB, 4, CSW>(tb, xb0, fb, swb, my, active);
+    if (__all_sync(kAll, run <= 3)) roi_warp_body_bwd<P, XB, 3, CSW>(tb, xb0, fb, swb, my, active);
+    else if (__all_sync(kAll, run == 4)) roi_warp_body_bwd<P, XB, 4, CSW>(tb, xb0, fb, swb, my, active);
     else roi_warp_body_bwd<P, XB, 0, CSW>(tb, xb0, fb, swb, my, active);
   }
 }
@@ -1111,7 +1196,9 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e);
     configured_dev = dev;
   }
-  kern<<<blocks, WARPS * 32, smem, st>>>(p, out, groups, env_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1, ipw);
+  // flags: bit 0 = evict-first output stores, bit 1 = per-warp tables even when a RoI has exactly WARPS channel groups
+  const int flags = (env_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (env_is("LCR_ROI_SHARED_TABLES", "0") ? 2 : 0);
+  kern<<<blocks, WARPS * 32, smem, st>>>(p, out, groups, flags, ipw);
   return after_launch();
 }
 
@@ -1134,7 +1221,7 @@ static int launch_bwd_warp(const RoiParams& p, const float* gout, cudaStream_t s
     if (e != cudaSuccess) return cuda_status(e);
     configured_dev = dev;
   }
-  kern<<<(unsigned)want, WARPS * 32, smem, st>>>(p, gout, groups, ipw);
+  kern<<<(unsigned)want, WARPS * 32, smem, st>>>(p, gout, groups, env_is("LCR_ROI_SHARED_TABLES", "0") ? 2 : 0, ipw);
   return after_launch();
 }
 

@@ -68,7 +68,7 @@ def main():
         print(json.dumps(kw), flush=True)
 
     def setenv(env):
-        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB"):
+        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_ROI_SHARED_TABLES"):
             os.environ.pop(k, None)
         os.environ.update(env)
 
@@ -76,8 +76,9 @@ def main():
         bytes_roi = 4 * n_props * B.C * 49 + F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS
         ref = None
         for name, env in [("cta(r01)", {"LCR_ROI_FWD": "cta"}), ("warp,persistent", {"LCR_ROI_IPW": "0"}), ("warp,ipw1", {"LCR_ROI_IPW": "1"}),
-                          ("warp,ipw2", {"LCR_ROI_IPW": "2"}), ("warp,split32ch", {"LCR_ROI_SPLIT": "1"}),
-                          ("warp,split32ch,ipw4", {"LCR_ROI_SPLIT": "1", "LCR_ROI_IPW": "4"})]:
+                          ("warp,ipw2", {"LCR_ROI_IPW": "2"}), ("warp,ipw2,per-warp tables", {"LCR_ROI_IPW": "2", "LCR_ROI_SHARED_TABLES": "0"}),
+                          ("warp,ipw3", {"LCR_ROI_IPW": "3"}), ("warp,ipw4", {"LCR_ROI_IPW": "4"}),
+                          ("warp,split32ch", {"LCR_ROI_SPLIT": "1"})]:
             setenv(env)
             out = pipe.pool(feat, props.rois)
             torch.cuda.synchronize()

@@ -447,7 +447,8 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(F, world), "clocks": clocks,
             "e2e": {"value": n_items / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "api": f"pipeline.HostFedRegionPipeline.run (chunks of {runner.FC} frames, H2D overlapped with compute)",
+                    "ms_per_step": e2e_ms, "h2d_GBps": h2d / 1e9 / (e2e_ms * 1e-3),
+                    "bound": "PCIe host->device copy of the step's inputs (compute is hidden behind it)", "api": f"pipeline.HostFedRegionPipeline.run (chunks of {runner.FC} frames, H2D overlapped with compute)",
                     "d2h": "detection records + counts (pasted masks stay sharded in HBM, SURVEY §8e)",
                     "counts_match_resident_run": e2e_ok, "host_cores_bound_to_gpu_numa_node": len(numa_cores)},
             "gpu_launches": int(launches), "launch_mode": launch_mode, "roofline": roofline, "kernels": kernels, "nms_us_2000_boxes": nms_us, "nms_us_2000_boxes_eager": nms_us_eager,

@@ -77,8 +77,7 @@ def main():
         ref = None
         for name, env in [("cta(r01)", {"LCR_ROI_FWD": "cta"}), ("warp,persistent", {"LCR_ROI_IPW": "0"}), ("warp,ipw1", {"LCR_ROI_IPW": "1"}),
                           ("warp,ipw2", {"LCR_ROI_IPW": "2"}), ("warp,ipw2,per-warp tables", {"LCR_ROI_IPW": "2", "LCR_ROI_SHARED_TABLES": "0"}),
-                          ("warp,ipw3", {"LCR_ROI_IPW": "3"}), ("warp,ipw4", {"LCR_ROI_IPW": "4"}),
-                          ("warp,split32ch", {"LCR_ROI_SPLIT": "1"})]:
+                          ("warp,ipw3", {"LCR_ROI_IPW": "3"}), ("warp,ipw4", {"LCR_ROI_IPW": "4"})]:
             setenv(env)
             out = pipe.pool(feat, props.rois)
             torch.cuda.synchronize()
@@ -99,7 +98,7 @@ def main():
         gin = torch.empty((F, B.C, B.FH, B.FW), device=dev).contiguous(memory_format=torch.channels_last)
         bytes_bwd = 4 * n_props * B.C * 49 + 3 * F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS
         ref = None
-        for name, env in [("cta(r01)", {"LCR_ROI_BWD": "cta"}), ("warp", {}), ("warp,split32ch", {"LCR_ROI_SPLIT": "1"})]:
+        for name, env in [("cta(r01)", {"LCR_ROI_BWD": "cta"}), ("warp", {})]:
             setenv(env)
             ops.roi_align_bwd(gout, [gin], [0.25], props.rois, None, 2, False, zero_grad=True)
             torch.cuda.synchronize()

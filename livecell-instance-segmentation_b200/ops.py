@@ -22,6 +22,29 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _NullCtx:
+    __slots__ = ()
+
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _dev(device):
+    """Device guard that costs nothing when `device` is already current (the common single-GPU-per-process case);
+    torch.cuda.device() alone is ~10 us per call, which matters for the small-K training shapes."""
+    device = torch.device(device)
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(device)
+
+
 def _need_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -76,7 +99,7 @@ def anchors(h: int, w: int, stride: int, base, device) -> torch.Tensor:
     arr = _base_array(base)
     A = len(arr) // 4
     out = torch.empty((h * w * A, 4), dtype=torch.float32, device=device)
-    with torch.cuda.device(device):
+    with _dev(device):
         check(_lib.load().lcr_anchors_f32(out.data_ptr(), h, w, stride, arr, A, _stream()), "anchors")
     return out
 
@@ -91,7 +114,7 @@ def clip_boxes_(boxes: torch.Tensor, img_h: float, img_w: float) -> torch.Tensor
         clip_boxes_(tmp, img_h, img_w)
         boxes.copy_(tmp)
         return boxes
-    with torch.cuda.device(boxes.device):
+    with _dev(boxes.device):
         check(_lib.load().lcr_clip_boxes_f32(boxes.data_ptr(), boxes.shape[0], float(img_h), float(img_w), _stream()), "clip")
     return boxes
 
@@ -102,7 +125,7 @@ def filter_small_boxes(boxes: torch.Tensor, min_size: float) -> torch.Tensor:
     b = _f32c(boxes)
     keep = torch.empty((b.shape[0],), dtype=torch.uint8, device=b.device)
     if b.shape[0]:
-        with torch.cuda.device(b.device):
+        with _dev(b.device):
             check(_lib.load().lcr_filter_small_boxes_f32(b.data_ptr(), b.shape[0], float(min_size), keep.data_ptr(), _stream()),
                   "filter_small_boxes")
     return keep.view(torch.bool)
@@ -117,7 +140,7 @@ def box_decode(deltas: torch.Tensor, anc: torch.Tensor, weights=(1.0, 1.0, 1.0, 
     w = (C.c_float * 4)(*[float(v) for v in weights])
     ih, iw = (0.0, 0.0) if img_size is None else (float(img_size[0]), float(img_size[1]))
     if a.shape[0]:
-        with torch.cuda.device(a.device):
+        with _dev(a.device):
             check(_lib.load().lcr_box_decode_f32(d.data_ptr(), a.data_ptr(), a.shape[0], w, float(xform_clip), ih, iw,
                                                  out.data_ptr(), _stream()), "box_decode")
     return out
@@ -171,7 +194,7 @@ def rpn_select(objectness: Sequence[torch.Tensor], *, k: int, img_size, score_th
     index = torch.empty((B, L, k), dtype=torch.int64, device=dev)
     counts = torch.empty((B, L), dtype=torch.int32, device=dev)
     lib = _lib.load()
-    with torch.cuda.device(dev):
+    with _dev(dev):
         nbytes = lib.lcr_rpn_select_workspace_bytes(B, L, k)
         ws = _workspace(nbytes, dev)
         check(lib.lcr_rpn_select_f32(levels, L, B, C.byref(cfg), boxes.data_ptr(), scores.data_ptr(), index.data_ptr(),
@@ -196,7 +219,7 @@ def nms_batched(boxes: torch.Tensor, scores: Optional[torch.Tensor], iou_thresho
     if S == 0 or stride == 0:
         return keep, kc
     lib = _lib.load()
-    with torch.cuda.device(b.device):
+    with _dev(b.device):
         nbytes = lib.lcr_nms_workspace_bytes(S, stride)
         ws = _workspace(nbytes, b.device)
         check(lib.lcr_nms_f32(b.data_ptr(), _ptr(s), _ptr(cat), _ptr(cn), S, stride, float(iou_threshold),
@@ -219,7 +242,7 @@ def gather_kept(boxes: torch.Tensor, scores: Optional[torch.Tensor], keep: torch
     rois = torch.empty((S * post_n, 5), dtype=torch.float32, device=b.device) if want_rois else None
     valid = torch.empty((S * post_n,), dtype=torch.uint8, device=b.device) if want_valid else None
     if S:
-        with torch.cuda.device(b.device):
+        with _dev(b.device):
             check(_lib.load().lcr_gather_kept_f32(b.data_ptr(), _ptr(s), keep.data_ptr(), keep_counts.data_ptr(), S, in_stride,
                                                   post_n, ob.data_ptr(), _ptr(osc), _ptr(rois), _ptr(valid), _stream()),
                   "gather_kept")
@@ -236,7 +259,7 @@ def level_map(boxes: torch.Tensor, k_min: int = 2, k_max: int = 5, canonical_sca
     K, bs = b.shape
     lv = torch.empty((K,), dtype=torch.int32, device=b.device)
     if K:
-        with torch.cuda.device(b.device):
+        with _dev(b.device):
             check(_lib.load().lcr_level_map_f32(b.data_ptr(), bs, K, k_min, k_max, float(canonical_scale), canonical_level,
                                                 float(eps), lv.data_ptr(), _stream()), "level_map")
     return lv
@@ -251,7 +274,7 @@ def to_nhwc(x: torch.Tensor) -> torch.Tensor:
         return x
     xc = _f32c(x)
     out = torch.empty_strided((N, Cc, H, W), (H * W * Cc, 1, W * Cc, Cc), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _dev(x.device):
         check(_lib.load().lcr_nchw_to_nhwc_f32(xc.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream()), "nchw_to_nhwc")
     return out
 
@@ -265,7 +288,7 @@ def to_nchw(x: torch.Tensor) -> torch.Tensor:
     if x.stride() != (H * W * Cc, 1, W * Cc, Cc):
         return x.contiguous()
     out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _dev(x.device):
         check(_lib.load().lcr_nhwc_to_nchw_f32(x.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream()), "nhwc_to_nchw")
     return out
 
@@ -308,7 +331,7 @@ def roi_align_fwd(feats: Sequence[torch.Tensor], scales: Sequence[float], rois: 
     if K == 0:
         return out
     lvl = None if roi_level is None else roi_level.to(torch.int32).contiguous()
-    with torch.cuda.device(r.device):
+    with _dev(r.device):
         check(_lib.load().lcr_roi_align_fwd_f32(_feat_levels(feats, scales), len(feats), Cc, r.data_ptr(), _ptr(lvl), K, PH, PW,
                                                 int(sampling_ratio), 1 if aligned else 0, out.data_ptr(), _stream()),
               "roi_align_fwd")
@@ -327,7 +350,7 @@ def roi_align_bwd(grad_out: torch.Tensor, grads: Sequence[torch.Tensor], scales:
             raise _lib.LcrError("roi_align_bwd: grad buffers must be dense fp32 (NCHW or channels_last)")
     K, Cc, PH, PW = g.shape
     lvl = None if roi_level is None else roi_level.to(torch.int32).contiguous()
-    with torch.cuda.device(g.device):
+    with _dev(g.device):
         check(_lib.load().lcr_roi_align_bwd_f32(g.data_ptr(), _feat_levels(grads, scales), len(grads), Cc, r.data_ptr(), _ptr(lvl),
                                                 K, PH, PW, int(sampling_ratio), 1 if aligned else 0, 1 if zero_grad else 0,
                                                 _stream()), "roi_align_bwd")
@@ -347,7 +370,7 @@ def paste_masks(probs: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int
         raise _lib.LcrError("paste_masks: out must be a contiguous uint8 buffer of at least N*H*W bytes")
     v = None if valid is None else valid.to(torch.uint8).contiguous()
     if N:
-        with torch.cuda.device(b.device):
+        with _dev(b.device):
             check(_lib.load().lcr_paste_masks_u8(p.data_ptr(), b.data_ptr(), _ptr(v), N, M, img_h, img_w, float(threshold),
                                                  int(on_value), out.data_ptr(), _stream()), "paste_masks")
     return out
@@ -361,7 +384,7 @@ def pack_records(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor
     cn = counts.to(torch.int32).contiguous()
     rec = torch.empty((S, stride, 6), dtype=torch.float32, device=b.device)
     if S:
-        with torch.cuda.device(b.device):
+        with _dev(b.device):
             check(_lib.load().lcr_pack_records_f32(b.data_ptr(), s.data_ptr(), cn.data_ptr(), S, stride, rec.data_ptr(), _stream()),
                   "pack_records")
     return rec
@@ -376,7 +399,7 @@ def box_iou(boxes: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
     N, G = a.shape[0], b.shape[0]
     out = torch.empty((N, G), dtype=torch.float32, device=a.device)
     if N and G:
-        with torch.cuda.device(a.device):
+        with _dev(a.device):
             check(_lib.load().lcr_box_iou_f32(a.data_ptr(), N, b.data_ptr(), G, out.data_ptr(), _stream()), "box_iou")
     return out
 
@@ -392,7 +415,7 @@ def box_iou_max(boxes: torch.Tensor, gt: torch.Tensor):
     mx = torch.empty((N,), dtype=torch.float32, device=a.device)
     am = torch.empty((N,), dtype=torch.int64, device=a.device)
     if N:
-        with torch.cuda.device(a.device):
+        with _dev(a.device):
             check(_lib.load().lcr_box_iou_max_f32(a.data_ptr(), N, b.data_ptr(), G, mx.data_ptr(), am.data_ptr(), _stream()),
                   "box_iou_max")
     return mx, am
@@ -412,7 +435,7 @@ def mask_targets(gt_masks: torch.Tensor, boxes: torch.Tensor, gt_index: Optional
     if K:
         if G == 0:
             raise _lib.LcrError("mask_targets: no ground-truth masks")
-        with torch.cuda.device(b.device):
+        with _dev(b.device):
             check(_lib.load().lcr_mask_targets_f32(m.data_ptr(), G, H, W, b.data_ptr(), _ptr(idx), K, int(mask_size), out.data_ptr(),
                                                    _stream()), "mask_targets")
     return out
@@ -429,7 +452,7 @@ def mask_tail(mask_logits: torch.Tensor, mask_size: int = 28, cls: int = 1) -> t
         raise _lib.LcrError("mask_tail: square mask logits expected")
     out = torch.empty((K, mask_size, mask_size), dtype=torch.float32, device=x.device)
     if K:
-        with torch.cuda.device(x.device):
+        with _dev(x.device):
             check(_lib.load().lcr_mask_tail_f32(x.data_ptr(), K, Cc, int(cls), m, int(mask_size), out.data_ptr(), _stream()), "mask_tail")
     return out
 
@@ -449,7 +472,7 @@ def mask_region_counts(masks: torch.Tensor, rects: torch.Tensor, rect_offsets: t
     total = torch.zeros((N,), dtype=torch.int32, device=m.device)
     inreg = torch.zeros((max(r.shape[0], 1),), dtype=torch.int32, device=m.device)
     if N:
-        with torch.cuda.device(m.device):
+        with _dev(m.device):
             check(_lib.load().lcr_mask_region_counts_u8(m.data_ptr(), N, H, W, _ptr(b), r.data_ptr() if r.numel() else None, ro.data_ptr(),
                                                         int(threshold), total.data_ptr(), inreg.data_ptr(), _stream()),
                   "mask_region_counts")

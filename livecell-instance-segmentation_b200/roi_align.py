@@ -54,15 +54,18 @@ class _RoIAlignFn(torch.autograd.Function):
             used.append(f)
         out = ops.roi_align_fwd(used, scales, rois, roi_level, (PH, PW), sampling_ratio, aligned)
         ctx.meta = (scales, output_size, sampling_ratio, aligned, [tuple(f.shape) for f in feats])
-        ctx.save_for_backward(rois, roi_level if roi_level is not None else torch.empty(0, device=rois.device))
+        if roi_level is None:
+            ctx.save_for_backward(rois)
+        else:
+            ctx.save_for_backward(rois, roi_level)
         ctx.has_level = roi_level is not None
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         scales, output_size, sampling_ratio, aligned, shapes = ctx.meta
-        rois, roi_level = ctx.saved_tensors
-        roi_level = roi_level if ctx.has_level else None
+        rois = ctx.saved_tensors[0]
+        roi_level = ctx.saved_tensors[1] if ctx.has_level else None
         grads = []
         for (N, C, H, W) in shapes:
             # channels_last grad buffers: the backward fast path scatters whole channel vectors

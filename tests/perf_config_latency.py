@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """BASELINE configs C1 and C3: the region path on ONE 704x520 frame (latency view; bench.py is the throughput view).
 
-    python tools/config_latency.py > gpurun_out/config_latency.jsonl
+    python tests/perf_config_latency.py > gpurun_out/config_latency.jsonl
+
+(Lives under tests/ — not collected by pytest — because it times the CPU oracle next to the GPU path, and only
+tests/, smoke() and bench.py's CPU legs may touch oracle/.)
 
 C1: reference defaults (top-k 250 -> <= 50 proposals -> <= 50 detections, ~150 cells).
 C3: crowded (2000 cells, top-k 2000 -> 1000 proposals -> 500 detections).

@@ -175,13 +175,17 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, in
     if (w >= rb && w * 32 < n) {
       const int col = w * 32 + lane;
       const bool col_ok = col < n;
+      const bool diag_word = (w == rb);
       float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
       if (col_ok) cb = boxes[col];
       const float carea = __fmul_rn(__fsub_rn(cb.z, cb.x), __fsub_rn(cb.w, cb.y));
       const int ccat = (use_cat && col_ok) ? cats[col] : 0;
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) {
-        const bool hit = col_ok && (col > row0 + r) && (!use_cat || ccat == row_cat[r]) &&
+        // upper triangle only, except the 32x32 diagonal block, which is stored symmetric (minus the diagonal): the
+        // resolve kernel then reads, for box b, the EARLIER boxes of its chunk that suppress it from b's own word
+        const bool wanted = diag_word ? (col != row0 + r) : (col > row0 + r);
+        const bool hit = col_ok && wanted && (!use_cat || ccat == row_cat[r]) &&
                          iou_gt<NEG_THR>(row_box[r], row_area[r], cb, carea, thr);
         const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit);
         if (lane == r) my_word = word;
@@ -201,10 +205,10 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, in
 
 // ---------------------------------------------------------------------------------------------
 // 3. resolve.  grid S, one CTA of kResolveThreads per segment.
-// Warp 0 owns the serial part (greedy pass over the chunk's 32x32 diagonal block: the 32 diagonal
-// words are broadcast with shuffles up front, the dependent chain is two LOP3 per box); all warps
-// then OR the rows of the kept boxes into the `removed` bit-vector (lane = row, warp = word slot,
-// redux.sync).  The row words are loaded one chunk ahead of the greedy pass, speculatively for all 32
+// Warp 0 owns the serial part (greedy pass over the chunk's 32x32 diagonal block, evaluated as a
+// ballot fixpoint on the symmetric block: 2-4 rounds instead of a 32-step chain); all warps
+// then OR the rows of the kept boxes into the `removed` bit-vector (warp = row pair, lane = word,
+// coalesced row segments + shared-memory atomicOr).  The row words are loaded one chunk ahead of the greedy pass, speculatively for all 32
 // rows, so no L2 round trip sits on the per-chunk critical path.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxWords = LCR_MAX_NMS_BOXES / 32;
@@ -226,70 +230,97 @@ __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int stride
 
   for (int w = tid; w < nchunks; w += kResolveThreads) removed[w] = 0u;
   int count = 0;
-  uint32_t diag = (warp == 0 && nchunks > 0 && lane < n) ? __ldg(mask + (size_t)lane * nw) : 0u;
+  // diagonal words (symmetric 32x32 block of the chunk), two chunks ahead
+  auto load_diag = [&](int c) -> uint32_t {
+    const int row = (c << 5) + lane;
+    return (warp == 0 && c < nchunks && row < n) ? __ldg(mask + (size_t)row * nw + c) : 0u;
+  };
+  uint32_t diag0 = load_diag(0), diag1 = load_diag(1);
+  // original indices of the chunk's boxes, also two chunks ahead (a load -> store dependency inside the chunk loop
+  // would put an L2 round trip on warp 0's critical path)
+  auto load_order = [&](int c) -> int {
+    const int row = (c << 5) + lane;
+    return (warp == 0 && row < n) ? __ldg(order + row) : 0;
+  };
+  int ord0 = load_order(0), ord1 = load_order(1);
 
-  // Row words of chunk c for this thread (lane = row of the chunk, warp = word slot): issued one chunk AHEAD,
-  // before the kept set is known, so the L2 round trip overlaps the serial greedy pass of warp 0.
+  // Row words of chunk c, issued TWO chunks ahead and speculatively for all 32 rows, so no L2 round trip sits on the
+  // per-chunk critical path.  Layout: warp w owns rows 2w and 2w+1 of the chunk, lane l owns words c+1+l and c+33+l of
+  // those rows — every load is a coalesced 128-byte row segment (a lane = row layout costs 32 L1 tag cycles per
+  // load and made the L1 the bottleneck: 2 000 cycles per chunk).
+  constexpr int kRowsPerWarp = 32 / kResolveWarps;  // 2
   auto prefetch = [&](int c, uint32_t (&v)[kResolveWpt]) {
-    const int row = min((c << 5) + lane, n - 1);  // rows past n: clamped, their kept bit is 0
-    const uint32_t* mrow = mask + (size_t)row * nw;
 #pragma unroll
-    for (int j = 0; j < kResolveWpt; ++j) {
-      const int w = c + 1 + warp + j * kResolveWarps;
-      v[j] = (c < nchunks && w < nchunks) ? __ldg(mrow + w) : 0u;
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const int row = min((c << 5) + warp * kRowsPerWarp + r, max(n - 1, 0));  // rows past n: clamped, their kept bit is 0
+      const uint32_t* mrow = mask + (size_t)row * nw;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int w = c + 1 + lane + 32 * j;
+        v[r * 2 + j] = (c < nchunks && w < nchunks) ? __ldg(mrow + w) : 0u;
+      }
     }
   };
-  uint32_t v[kResolveWpt];
-  prefetch(0, v);
+  uint32_t v0[kResolveWpt], v1[kResolveWpt];
+  prefetch(0, v0);
+  prefetch(1, v1);
   __syncthreads();
 
   for (int c = 0; c < nchunks && count < post_n; ++c) {
     const int row0 = c << 5;
     if (warp == 0) {
-      // prefetch the next chunk's diagonal word (address is data-independent)
-      const int nrow = row0 + 32 + lane;
-      const uint32_t diag_next = (c + 1 < nchunks && nrow < n) ? __ldg(mask + (size_t)nrow * nw + (c + 1)) : 0u;
+      const uint32_t diag2 = load_diag(c + 2);
+      const int ord2 = load_order(c + 2);
       const int left = n - row0;
       const uint32_t in_range = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
-      uint32_t alive = ~removed[c] & in_range;
-      uint32_t d[32];
-#pragma unroll
-      for (int b = 0; b < 32; ++b) d[b] = __shfl_sync(0xFFFFFFFFu, diag, b);
-      uint32_t kept = 0u;
-#pragma unroll
-      for (int b = 0; b < 32; ++b) {
-        if ((alive >> b) & 1u) {
-          kept |= 1u << b;
-          alive &= ~d[b];
-        }
+      const uint32_t alive = ~removed[c] & in_range;
+      // Greedy pass over the chunk as a fixpoint: box b is kept iff it is alive and no KEPT earlier box of the chunk
+      // suppresses it.  Starting from kept = alive, box b is final after b+1 rounds at the latest (it only depends on
+      // earlier boxes); in practice the dependency chains are 2-3 boxes deep, so the loop runs 2-4 ballots instead
+      // of a 32-step serial chain.
+      const uint32_t earlier = diag0 & ((1u << lane) - 1u);
+      const bool me = (alive >> lane) & 1u;
+      uint32_t kept = alive;
+      for (int it = 0; it < 32; ++it) {
+        const uint32_t nk = __ballot_sync(0xFFFFFFFFu, me && !(earlier & kept));
+        if (nk == kept) break;
+        kept = nk;
       }
       if ((kept >> lane) & 1u) {  // emit the kept boxes of this chunk in order
         const int pos = count + __popc(kept & ((1u << lane) - 1u));
-        if (pos < post_n) out[pos] = (int64_t)order[row0 + lane];
+        if (pos < post_n) out[pos] = (int64_t)ord0;
       }
       if (lane == 0) s_kept = kept;
-      diag = diag_next;
+      diag0 = diag1;
+      diag1 = diag2;
+      ord0 = ord1;
+      ord1 = ord2;
     }
     __syncthreads();
     const uint32_t kept = s_kept;
     count += __popc(kept);
-    uint32_t vn[kResolveWpt];
-    prefetch(c + 1, vn);  // in flight while this chunk is folded and the next greedy pass runs
-    const bool row_kept = (kept >> lane) & 1u;
+    uint32_t v2[kResolveWpt];
+    prefetch(c + 2, v2);  // in flight during this fold and the next chunk
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      if ((kept >> (warp * kRowsPerWarp + r)) & 1u) {  // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int w = c + 1 + lane + 32 * j;
+          if (w < nchunks && v0[r * 2 + j]) atomicOr(&removed[w], v0[r * 2 + j]);
+        }
+        // segments longer than 2048 boxes: the remaining words of the kept rows, loaded on demand
+        for (int w = c + 1 + lane + 64; w < nchunks; w += 32) {
+          const uint32_t x = __ldg(mask + (size_t)(row0 + warp * kRowsPerWarp + r) * nw + w);
+          if (x) atomicOr(&removed[w], x);
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < kResolveWpt; ++j) {
-      const int w = c + 1 + warp + j * kResolveWarps;
-      const uint32_t acc = __reduce_or_sync(0xFFFFFFFFu, row_kept ? v[j] : 0u);
-      if (lane == 0 && w < nchunks) removed[w] |= acc;
+      v0[j] = v1[j];
+      v1[j] = v2[j];
     }
-    // segments longer than 2048 boxes: the remaining words of the kept rows, loaded on demand
-    for (int w0 = c + 1 + warp + kResolveWpt * kResolveWarps; w0 < nchunks; w0 += kResolveWarps) {
-      const uint32_t x = row_kept ? __ldg(mask + (size_t)(row0 + lane) * nw + w0) : 0u;
-      const uint32_t acc = __reduce_or_sync(0xFFFFFFFFu, x);
-      if (lane == 0) removed[w0] |= acc;
-    }
-#pragma unroll
-    for (int j = 0; j < kResolveWpt; ++j) v[j] = vn[j];
     __syncthreads();
   }
   if (tid == 0) keep_counts[s] = min(count, post_n);

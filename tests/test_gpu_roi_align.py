@@ -130,3 +130,30 @@ def test_layout_helpers(ops, synth):
     assert np.array_equal(N(y), x)
     z = ops.to_nchw(y)
     assert z.is_contiguous() and np.array_equal(N(z), x)
+
+
+@pytest.mark.parametrize("P", [7, 14])
+def test_multilevel_fpn_rois_vs_oracle(ops, oracle, synth, P):
+    """MultiScaleRoIAlign semantics (TV:ops/poolers.py:147-227) at the C5 geometry: 4 FPN levels of a 704x520 frame,
+    64 channels, RoIs of 12-400 px assigned by the level mapper, box (7x7) and mask (14x14) pooling, forward and
+    backward against the oracle — one launch for all levels."""
+    from gpu_util import N, T, nhwc, assert_close_rel
+    shapes, scales, C, K = [(130, 176), (65, 88), (33, 44), (17, 22)], [0.25, 0.125, 0.0625, 0.03125], 64, 300
+    feats = [synth.make_features(1, C, h, w, seed=60 + i) for i, (h, w) in enumerate(shapes)]
+    rois = synth.make_rois(K, 61, mode="fpn", edge_cases=True)
+    lv_ref = oracle.level_map(rois[:, 1:])
+    lvl = ops.level_map(T(rois), 2, 5, 224.0, 4)
+    assert np.array_equal(N(lvl), lv_ref) and len(set(lv_ref.tolist())) >= 3          # the RoIs really spread over levels
+    ref = oracle.multiscale_roi_align_fwd(feats, scales, rois, lv_ref, P, P, 2, False)
+    out = ops.roi_align_fwd([nhwc(T(f)) for f in feats], scales, T(rois), lvl, (P, P), 2, False)
+    assert_close_rel(N(out), ref, RTOL)
+    out2 = ops.roi_align_fwd([T(f) for f in feats], scales, T(rois), lvl, (P, P), 2, False)     # NCHW: generic kernel
+    assert_close_rel(N(out2), ref, RTOL)
+    rng = np.random.RandomState(62)
+    go = rng.standard_normal((K, C, P, P)).astype(np.float32)
+    grads = [torch.empty((1, C, h, w), device="cuda:0").contiguous(memory_format=torch.channels_last) for h, w in shapes]
+    ops.roi_align_bwd(T(go), grads, scales, T(rois), lvl, 2, False, zero_grad=True)
+    for l, (h, w) in enumerate(shapes):
+        sel = lv_ref == l
+        ref_b = oracle.roi_align_bwd(go[sel], rois[sel], (1, C, h, w), scales[l], 2, False) if sel.any() else np.zeros((1, C, h, w), np.float32)
+        assert_close_rel(N(grads[l]), ref_b, RTOL)

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, in
 constexpr int kMaxWords = LCR_MAX_NMS_BOXES / 32;
 constexpr int kResolveThreads = 512;
 constexpr int kResolveWarps = kResolveThreads / 32;
-constexpr int kResolveWpt = 4;  // mask words per thread held in registers (covers 16*4 = 64 words = 2048 boxes per pass)
+constexpr int kResolveWpt = 2 * (32 / kResolveWarps);  // mask words per thread held in registers: its rows x 2 word groups (2048 boxes per pass)
 
 __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int stride, int post_n, NmsWorkspace ws,
                                                                       int64_t* __restrict__ keep, int* __restrict__ keep_counts) {

@@ -142,7 +142,7 @@ static float float_threshold(double thr) {
 }
 
 template <bool NEG_THR>
-__global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, int use_cat, NmsWorkspace ws) {
+__global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, int use_cat, int span, NmsWorkspace ws) {
   __shared__ float4 row_box[32];
   __shared__ float row_area[32];
   __shared__ int row_cat[32];
@@ -151,9 +151,9 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, in
   const int s = blockIdx.z, rb = blockIdx.y, sp = blockIdx.x;
   const int n = ws.n_valid[s];
   const int row0 = rb * 32;
-  const int w_lo = sp * 32;
+  const int w_lo = sp * span;  // span = mask words per CTA: 32 when many segments fill the GPU, 8 for one segment (latency)
   // nothing to do for empty row blocks or spans entirely below the diagonal / beyond n
-  if (row0 >= n || w_lo + 31 < rb || w_lo * 32 >= n) return;
+  if (row0 >= n || w_lo + span - 1 < rb || w_lo * 32 >= n) return;
 
   const float4* boxes = ws.sorted_boxes + (size_t)s * stride;
   const int* cats = ws.sorted_cat + (size_t)s * stride;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, in
   }
   __syncthreads();
 
-  for (int wl = warp; wl < 32; wl += 8) {
+  for (int wl = warp; wl < span; wl += 8) {
     const int w = w_lo + wl;
     uint32_t my_word = 0u;  // lane r ends up holding the word of row r
     if (w >= rb && w * 32 < n) {
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, in
   for (int r = warp; r < 32; r += 8) {
     const int row = row0 + r;
     const int w = w_lo + lane;
-    if (row < n && w < nw) ws.mask[((size_t)s * stride + row) * nw + w] = words[r][lane];
+    if (row < n && w < nw && lane < span) ws.mask[((size_t)s * stride + row) * nw + w] = words[r][lane];
   }
 }
 
@@ -356,11 +356,16 @@ extern "C" int lcr_nms_f32(const float* boxes, const float* scores, const int* c
   if (rc != LCR_OK) return rc;
 
   const int row_blocks = (stride + 31) / 32;
-  const int spans = (ws.nw + 31) / 32;
+  int span = ((long long)S * row_blocks * ((ws.nw + 31) / 32) >= 4ll * sm_count()) ? 32 : 8;
+  if (const char* v = getenv("LCR_NMS_SPAN")) {  // tuning switch for A/B runs (tools/bench_kernels.py)
+    const int e = atoi(v);
+    if (e == 8 || e == 16 || e == 32) span = e;
+  }
+  const int spans = (ws.nw + span - 1) / span;
   dim3 g2(spans, row_blocks, S);
   const float tf = float_threshold(iou_threshold);
-  if (tf < 0.f) nms_mask_kernel<true><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, ws);
-  else nms_mask_kernel<false><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, ws);
+  if (tf < 0.f) nms_mask_kernel<true><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, span, ws);
+  else nms_mask_kernel<false><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, span, ws);
   rc = after_launch();
   if (rc != LCR_OK) return rc;
 

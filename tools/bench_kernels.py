@@ -68,7 +68,7 @@ def main():
         print(json.dumps(kw), flush=True)
 
     def setenv(env):
-        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_ROI_SHARED_TABLES"):
+        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN"):
             os.environ.pop(k, None)
         os.environ.update(env)
 
@@ -169,6 +169,23 @@ def main():
         emit(kernel="nms(64 segments x 2000)", variant="default", ms=med, ms_min=mn)
         med, mn = timed(lambda: ops.nms_batched(bx[:1], None, 0.4, post_n=B.POST_NMS, counts=ct[:1]), args.reps)
         emit(kernel="nms(1 segment x 2000)", variant="default", us=med * 1e3, us_min=mn * 1e3)
+        # single-segment latency without the Python launch path: the three launches replayed from a CUDA graph
+        bx1, ct1 = bx[:1].contiguous(), ct[:1].contiguous()
+        for name, env in [("span8", {"LCR_NMS_SPAN": "8"}), ("span16", {"LCR_NMS_SPAN": "16"}), ("span32", {"LCR_NMS_SPAN": "32"})]:
+            setenv(env)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    ops.nms_batched(bx1, None, 0.4, post_n=B.POST_NMS, counts=ct1)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                keep_g, kc_g = ops.nms_batched(bx1, None, 0.4, post_n=B.POST_NMS, counts=ct1)
+            med, mn = timed(gr.replay, max(args.reps, 50))
+            emit(kernel="nms(1 segment x 2000), graph replay", variant=name, us=med * 1e3, us_min=mn * 1e3, kept=int(kc_g[0]))
+        setenv({})
         med, mn = timed(lambda: ops.nms_batched(props.boxes, bs_d, 0.5, post_n=B.MAX_DET, counts=props.counts, score_thresh=0.4), args.reps)
         emit(kernel="det nms(64 segments x 1000, scores)", variant="default", ms=med, ms_min=mn)
 

@@ -19,11 +19,22 @@
 //                          the kept boxes are OR-ed into the `removed` bit-vector (shared memory),
 //                          loads for the next chunk being issued before the serial part.
 //                          Stops as soon as post_n boxes are kept.
+//   3'. nms_jacobi_kernel  segments of <= 2048 boxes: the greedy keep vector is the unique solution of the
+//                          triangular system kept[i] = !OR_{j<i}(M[i][j] & kept[j]); one thread per box holds its
+//                          (lower-triangle) mask row in registers and the whole vector is re-evaluated in parallel
+//                          rounds (a cluster of 8 CTAs exchanges the 64 kept words through distributed shared
+//                          memory) until it stops changing — 5-7 rounds on crowded scenes instead of a
+//                          63-chunk serial chain, exact by induction over the box index.
 //
 // Bound: latency (N <= 2000 boxes, 20 B each) — reported in microseconds, not GB/s.
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace lcr {
 
@@ -39,7 +50,7 @@ struct NmsWorkspace {
 };
 
 static size_t nms_ws_layout(int S, int stride, void* base, NmsWorkspace* ws) {
-  const int nw = (stride + 31) / 32;
+  const int nw = ((stride + 31) / 32 + 3) & ~3;  // row pitch in words: 16-byte aligned rows (uint4 row loads)
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -142,7 +153,7 @@ static float float_threshold(double thr) {
 }
 
 template <bool NEG_THR>
-__global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, int use_cat, int span, NmsWorkspace ws) {
+__global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, int use_cat, int span, int lower, NmsWorkspace ws) {
   __shared__ float4 row_box[32];
   __shared__ float row_area[32];
   __shared__ int row_cat[32];
@@ -190,6 +201,20 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, in
         const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit);
         if (lane == r) my_word = word;
       }
+      if (lower && !diag_word) {
+        // the mirror image for the parallel resolve: row (32w + c) gets, as its word rb, the rows of this block that
+        // suppress column c — a 32x32 bit transpose by ballots, lane c keeping the ballot of bit c
+        // (most blocks are empty and the rest hold a few bits: only the columns that occur are visited)
+        uint32_t t_word = 0u;
+        uint32_t cols = __reduce_or_sync(0xFFFFFFFFu, my_word);
+        while (cols) {
+          const int c = __ffs(cols) - 1;
+          cols &= cols - 1u;
+          const uint32_t word = __ballot_sync(0xFFFFFFFFu, (my_word >> c) & 1u);
+          if (lane == c) t_word = word;
+        }
+        if (col_ok) ws.mask[((size_t)s * stride + col) * ws.nw + rb] = t_word;
+      }
     }
     words[lane][wl] = my_word;
   }
@@ -199,7 +224,7 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(int stride, float thr, in
   for (int r = warp; r < 32; r += 8) {
     const int row = row0 + r;
     const int w = w_lo + lane;
-    if (row < n && w < nw && lane < span) ws.mask[((size_t)s * stride + row) * nw + w] = words[r][lane];
+    if (row < n && w < nw && lane < span && w >= rb) ws.mask[((size_t)s * stride + row) * nw + w] = words[r][lane];
   }
 }
 
@@ -326,6 +351,140 @@ __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int stride
   if (tid == 0) keep_counts[s] = min(count, post_n);
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3'. parallel resolve.  grid (CL, S), cluster (CL, 1, 1), 256 threads; segments of <= 256 * CL boxes.
+// Box i lives in 32-box block b = i / 32; block b belongs to CTA (b % CL), warp (b / CL), lane (i % 32).
+// The thread keeps words 0..b of its mask row in registers (the diagonal word cut to the earlier boxes).  A round
+// evaluates kept[i] = valid[i] && !OR_w(row[w] & K[w]) for every box at once against the previous round's vector K
+// (the block's own word is refined on the spot by the ballot fixpoint of the serial kernel, so after round t the
+// blocks 0..t-1 are final and the loop ends after at most nblocks + 1 rounds; crowded scenes take 5-7).  Every warp
+// stores its new word into the K buffers of all CTAs of the cluster (distributed shared memory) and raises a
+// cluster-wide `changed` flag; one cluster barrier per round.
+// ---------------------------------------------------------------------------------------------
+template <int NW4, int CL>
+__global__ void __launch_bounds__(256) nms_jacobi_kernel(int stride, int post_n, NmsWorkspace ws, int64_t* __restrict__ keep,
+                                                         int* __restrict__ keep_counts) {
+  constexpr int NW = NW4 * 4;
+  constexpr uint32_t kAll = 0xFFFFFFFFu;
+  __shared__ __align__(16) uint32_t K[2][NW];
+  __shared__ uint32_t chg[4];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int q = CL > 1 ? (int)cluster.block_rank() : 0;
+  const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(ws.n_valid[s], 32 * NW);
+  const int nw = ws.nw;
+  const int b = warp * CL + q;       // this warp's block
+  const int i = b * 32 + lane;       // this thread's box (sorted position)
+  const bool valid = i < n;
+  const uint32_t* mrow = ws.mask + ((size_t)s * stride + (valid ? i : 0)) * nw;
+  const int ord = valid ? __ldg(ws.order + (size_t)s * stride + i) : 0;
+
+  uint4 row[NW4];
+#pragma unroll
+  for (int j = 0; j < NW4; ++j) {
+    row[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (valid && 4 * j <= b) row[j] = __ldg(reinterpret_cast<const uint4*>(mrow) + j);
+  }
+  // words past the block are not part of the lower triangle (they hold the upper one): clear them; the diagonal
+  // word splits into the earlier boxes of the block (in-warp fixpoint) and nothing else
+  uint32_t earlier = 0u;
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < NW4; ++j) {
+    uint32_t* wv = reinterpret_cast<uint32_t*>(&row[j]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int w = 4 * j + e;
+      if (w == b) earlier = wv[e] & lt;
+      if (w >= b) wv[e] = 0u;
+    }
+  }
+  for (int w = tid; w < NW; w += 256) {
+    const int left = n - 32 * w;
+    const uint32_t v = left >= 32 ? kAll : (left > 0 ? (1u << left) - 1u : 0u);
+    K[0][w] = v;
+    K[1][w] = v;
+  }
+  if (tid < 4) chg[tid] = 0u;
+  if (CL > 1) cluster.sync();  // nobody stores into a peer's K / chg before the peer initialised them
+  else __syncthreads();
+
+  int cur = 0;
+  for (int r = 0;; ++r) {
+    uint32_t acc = 0u;
+    const uint4* kv = reinterpret_cast<const uint4*>(K[cur]);
+#pragma unroll
+    for (int j = 0; j < NW4; ++j) {
+      const uint4 k = kv[j];
+      acc |= (row[j].x & k.x) | (row[j].y & k.y) | (row[j].z & k.z) | (row[j].w & k.w);
+    }
+    const bool me = valid && acc == 0u;
+    uint32_t word = __ballot_sync(kAll, me);
+    for (int it = 0; it < 32; ++it) {  // greedy pass inside the block, as a fixpoint (2-4 ballots)
+      const uint32_t nk = __ballot_sync(kAll, me && !(earlier & word));
+      if (nk == word) break;
+      word = nk;
+    }
+    const int slot = r % 3;
+    if (b < NW) {
+      const bool changed = word != K[cur][b];
+      if (CL > 1) {
+        if (lane < CL) {
+          cluster.map_shared_rank(&K[cur ^ 1][0], lane)[b] = word;
+          if (changed) *cluster.map_shared_rank(&chg[slot], lane) = 1u;
+        }
+      } else if (lane == 0) {
+        K[cur ^ 1][b] = word;
+        if (changed) chg[slot] = 1u;
+      }
+    }
+    if (tid == 0) chg[(r + 1) % 3] = 0u;  // next round's flag: last read two barriers ago, first written after this one
+    if (CL > 1) cluster.sync();
+    else __syncthreads();
+    cur ^= 1;
+    if (chg[slot] == 0u) break;  // uniform over the cluster: every CTA received the same flags
+  }
+
+  // K[cur] is the keep vector.  Kept boxes go out in score order: position = kept boxes in earlier blocks + earlier
+  // kept boxes of the block.
+  const uint32_t* kf = K[cur];
+  int before = 0, total = 0;
+  for (int w = lane; w < NW; w += 32) {
+    const int c = __popc(kf[w]);
+    total += c;
+    if (w < b) before += c;
+  }
+  before = __reduce_add_sync(kAll, before);
+  total = __reduce_add_sync(kAll, total);
+  if (b < NW) {
+    const uint32_t word = kf[b];
+    if ((word >> lane) & 1u) {
+      const int pos = before + __popc(word & lt);
+      if (pos < post_n) keep[(size_t)s * post_n + pos] = (int64_t)ord;
+    }
+  }
+  if (q == 0 && tid == 0) keep_counts[s] = min(total, post_n);
+}
+
+template <int NW4, int CL>
+static int launch_jacobi(int S, int stride, int post_n, const NmsWorkspace& ws, int64_t* keep, int* keep_counts, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL, S, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, nms_jacobi_kernel<NW4, CL>, stride, post_n, ws, keep, keep_counts);
+  if (e != cudaSuccess) return cuda_status(e);
+  return after_launch();
+}
+
 }  // namespace lcr
 
 using namespace lcr;
@@ -364,11 +523,20 @@ extern "C" int lcr_nms_f32(const float* boxes, const float* scores, const int* c
   const int spans = (ws.nw + span - 1) / span;
   dim3 g2(spans, row_blocks, S);
   const float tf = float_threshold(iou_threshold);
-  if (tf < 0.f) nms_mask_kernel<true><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, span, ws);
-  else nms_mask_kernel<false><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, span, ws);
+  // segments of <= 2048 boxes: parallel (Jacobi) resolve on the full symmetric mask; longer ones: serial chunk walk
+  bool parallel = stride <= 2048;
+  if (const char* v = getenv("LCR_NMS_RESOLVE")) parallel = parallel && strcmp(v, "serial") != 0;  // tuning switch (A/B, tests)
+  if (tf < 0.f) nms_mask_kernel<true><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, span, parallel ? 1 : 0, ws);
+  else nms_mask_kernel<false><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, span, parallel ? 1 : 0, ws);
   rc = after_launch();
   if (rc != LCR_OK) return rc;
 
+  if (parallel) {
+    if (stride <= 256) return launch_jacobi<2, 1>(S, stride, post_n, ws, keep, keep_counts, st);
+    if (stride <= 512) return launch_jacobi<4, 8>(S, stride, post_n, ws, keep, keep_counts, st);
+    if (stride <= 1024) return launch_jacobi<8, 8>(S, stride, post_n, ws, keep, keep_counts, st);
+    return launch_jacobi<16, 8>(S, stride, post_n, ws, keep, keep_counts, st);
+  }
   nms_resolve_kernel<<<S, kResolveThreads, 0, st>>>(stride, post_n, ws, keep, keep_counts);
   return after_launch();
 }

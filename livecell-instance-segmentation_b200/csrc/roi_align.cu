@@ -25,6 +25,7 @@
 //
 // Roofline: HBM.  Algorithmic bytes fwd = 4*K*C*P*P (out) + unique feature bytes + 20*K.
 // Generic kernels (any strides / sampling ratio / pooled size) back every other configuration.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -742,7 +743,13 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
       bulk_commit();
     }
   }
-  if (lane == 0) bulk_wait_all();
+  // Only the tile READS have to finish before the CTA's shared memory goes away; the writes complete on their own
+  // before the grid does.  (wait_group without .read compiles to DEPBAR + CCTL.IVALL: every exiting CTA would
+  // invalidate the SM's L1 under the three CTAs still gathering through it.)
+  if (lane == 0) {
+    if (flags & 128) bulk_wait_all();
+    else bulk_wait_read_all();
+  }
 }
 
 // ---- backward -----------------------------------------------------------------------------------
@@ -1247,6 +1254,7 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
     sscanf(v, "%d,%d", &kind, &dist);
     flags |= (kind & 3) << 2 | (dist & 7) << 4;
   }
+  if (env_is("LCR_ROI_EXIT_WAIT", "all")) flags |= 128;  // A/B: the r01c exit path
   if (const char* v = getenv("LCR_ROI_CARVEOUT")) {  // tuning switch: shared-memory carve-out in percent (fewer CTAs, larger L1)
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v));
   }

@@ -67,6 +67,23 @@ def test_crowded_duplicates(oracle):
         assert np.array_equal(gpu_nms(boxes, scores, thr), oracle.nms(boxes, scores, thr))
 
 
+@pytest.mark.parametrize("n", [64, 700, 2048])
+def test_suppression_chain_depth(oracle, n):
+    """A staircase where every box overlaps only its successor above the threshold and scores fall along it: the keep
+    decision of box i depends on box i-1 (kept, dropped, kept, ...), the deepest dependency chain there is — the
+    parallel resolve needs its maximum number of rounds (one per 32-box block)."""
+    step = 10.0
+    x = np.arange(n, dtype=np.float32) * step
+    boxes = np.stack([x, np.zeros(n, np.float32), x + 40.0, np.full(n, 40.0, np.float32)], axis=1)   # IoU(i, i+1) = 0.6, (i, i+2) = 0.33
+    scores = np.arange(n, 0, -1).astype(np.float32)
+    for thr in (0.5, 0.3):
+        ref = oracle.nms(boxes, scores, thr)
+        assert np.array_equal(gpu_nms(boxes, scores, thr), ref), (n, thr)
+    rng = np.random.RandomState(n)   # the same staircase in shuffled input order
+    perm = rng.permutation(n)
+    assert np.array_equal(gpu_nms(boxes[perm], scores[perm], 0.5), oracle.nms(boxes[perm], scores[perm], 0.5))
+
+
 def test_batched_segments_counts_presorted_postn(ops, oracle, synth):
     from gpu_util import N, T
     S, stride = 5, 300

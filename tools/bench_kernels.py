@@ -68,7 +68,8 @@ def main():
         print(json.dumps(kw), flush=True)
 
     def setenv(env):
-        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN"):
+        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
+                  "LCR_ROI_PF", "LCR_ROI_CARVEOUT", "LCR_ROI_EXIT_WAIT", "LCR_NMS_RESOLVE"):
             os.environ.pop(k, None)
         os.environ.update(env)
 
@@ -77,7 +78,17 @@ def main():
         ref = None
         for name, env in [("cta(r01)", {"LCR_ROI_FWD": "cta"}), ("warp,persistent", {"LCR_ROI_IPW": "0"}), ("warp,ipw1", {"LCR_ROI_IPW": "1"}),
                           ("warp,ipw2", {"LCR_ROI_IPW": "2"}), ("warp,ipw2,per-warp tables", {"LCR_ROI_IPW": "2", "LCR_ROI_SHARED_TABLES": "0"}),
-                          ("warp,ipw3", {"LCR_ROI_IPW": "3"}), ("warp,ipw4", {"LCR_ROI_IPW": "4"})]:
+                          ("warp,ipw3", {"LCR_ROI_IPW": "3"}), ("warp,ipw4", {"LCR_ROI_IPW": "4"}),
+                          ("warp,ipw2,exit wait_group (r01c)", {"LCR_ROI_EXIT_WAIT": "all"}),
+                          ("warp,ipw2,prefetch.L1 dist1", {"LCR_ROI_PF": "1,1"}), ("warp,ipw2,prefetch.L1 dist2", {"LCR_ROI_PF": "1,2"}),
+                          ("warp,ipw2,prefetch.L1 dist3", {"LCR_ROI_PF": "1,3"}),
+                          ("warp,ipw2,dead-load dist1", {"LCR_ROI_PF": "2,1"}), ("warp,ipw2,dead-load dist2", {"LCR_ROI_PF": "2,2"}),
+                          ("warp,ipw2,carveout75", {"LCR_ROI_CARVEOUT": "75"}),
+                          ("warp,ipw2,carveout75,prefetch.L1 dist1", {"LCR_ROI_CARVEOUT": "75", "LCR_ROI_PF": "1,1"}),
+                          ("warp,ipw2,carveout75,prefetch.L1 dist2", {"LCR_ROI_CARVEOUT": "75", "LCR_ROI_PF": "1,2"}),
+                          ("warp,ipw2,carveout75,dead-load dist2", {"LCR_ROI_CARVEOUT": "75", "LCR_ROI_PF": "2,2"}),
+                          ("warp,ipw2,carveout50,prefetch.L1 dist2", {"LCR_ROI_CARVEOUT": "50", "LCR_ROI_PF": "1,2"}),
+                          ("warp,ipw2 (default again)", {"LCR_ROI_CARVEOUT": "-1"})]:
             setenv(env)
             out = pipe.pool(feat, props.rois)
             torch.cuda.synchronize()
@@ -165,13 +176,20 @@ def main():
         boxes, scores, _, counts = ops.rpn_select([obj_d], k=B.PRE_NMS, img_size=(B.IMG_H, B.IMG_W), score_thresh=0.3, min_size=10.0,
                                                   strides=[4], base=pipe.base)
         bx, ct = boxes[:, 0], counts[:, 0].contiguous()
-        med, mn = timed(lambda: ops.nms_batched(bx, None, 0.4, post_n=B.POST_NMS, counts=ct), args.reps)
-        emit(kernel="nms(64 segments x 2000)", variant="default", ms=med, ms_min=mn)
+        for name, env in [("serial resolve", {"LCR_NMS_RESOLVE": "serial"}), ("parallel resolve", {})]:
+            setenv(env)
+            med, mn = timed(lambda: ops.nms_batched(bx, None, 0.4, post_n=B.POST_NMS, counts=ct), args.reps)
+            emit(kernel="nms(64 segments x 2000)", variant=name, ms=med, ms_min=mn)
+            med, mn = timed(lambda: ops.nms_batched(props.boxes, bs_d, 0.5, post_n=B.MAX_DET, counts=props.counts, score_thresh=0.4), args.reps)
+            emit(kernel="det nms(64 segments x 1000, scores)", variant=name, ms=med, ms_min=mn)
+        setenv({})
         med, mn = timed(lambda: ops.nms_batched(bx[:1], None, 0.4, post_n=B.POST_NMS, counts=ct[:1]), args.reps)
         emit(kernel="nms(1 segment x 2000)", variant="default", us=med * 1e3, us_min=mn * 1e3)
         # single-segment latency without the Python launch path: the three launches replayed from a CUDA graph
         bx1, ct1 = bx[:1].contiguous(), ct[:1].contiguous()
-        for name, env in [("span8", {"LCR_NMS_SPAN": "8"}), ("span16", {"LCR_NMS_SPAN": "16"}), ("span32", {"LCR_NMS_SPAN": "32"})]:
+        for name, env in [("serial resolve, span8", {"LCR_NMS_RESOLVE": "serial", "LCR_NMS_SPAN": "8"}),
+                          ("parallel resolve, span8", {"LCR_NMS_SPAN": "8"}), ("parallel resolve, span16", {"LCR_NMS_SPAN": "16"}),
+                          ("parallel resolve, span32", {"LCR_NMS_SPAN": "32"})]:
             setenv(env)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())

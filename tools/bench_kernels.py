@@ -104,6 +104,31 @@ def main():
         del ref
         setenv({})
 
+    if "roiexp" in only:
+        # what bounds the forward kernel?  same launch, different RoI lists (time per item vs window size / locality)
+        r0 = props.rois.clone()
+        live = r0[:, 0] >= 0
+        def run(name, rois):
+            med, mn = timed(lambda: pipe.pool(feat, rois), args.reps, flush)
+            w = (rois[:, 3] - rois[:, 1])[live] * 0.25
+            h = (rois[:, 4] - rois[:, 2])[live] * 0.25
+            emit(kernel="roi_align_fwd experiment", variant=name, ms=med, ms_min=mn, mean_window_px=float(((w + 2) * (h + 2)).mean()))
+        run("real list", r0)
+        same = r0.clone()
+        same[:, 1:] = torch.tensor([100.0, 100.0, 164.0, 164.0], device=dev)
+        run("every RoI the same 64x64 box (all L1/L2 hits)", same)
+        for side in (32.0, 64.0, 128.0):
+            fx = r0.clone()
+            cx, cy = (r0[:, 1] + r0[:, 3]) / 2, (r0[:, 2] + r0[:, 4]) / 2
+            cx = cx.clamp(side / 2, B.IMG_W - side / 2)
+            cy = cy.clamp(side / 2, B.IMG_H - side / 2)
+            fx[:, 1], fx[:, 2], fx[:, 3], fx[:, 4] = cx - side / 2, cy - side / 2, cx + side / 2, cy + side / 2
+            run(f"real centres, every box {int(side)}x{int(side)}", fx)
+        # spatially sorted inside each frame (row-major 64-px cells): neighbours in the list overlap
+        key = r0[:, 0] * 1e6 + torch.floor((r0[:, 2] + r0[:, 4]) / 128) * 1e3 + (r0[:, 1] + r0[:, 3]) / 2
+        key = torch.where(live, key, torch.full_like(key, 1e12))
+        run("real boxes, spatially sorted per frame", r0[torch.argsort(key)].contiguous())
+
     if "bwd" in only:
         gout = torch.randn((F * B.POST_NMS, B.C, 7, 7), generator=g, device=dev)
         gin = torch.empty((F, B.C, B.FH, B.FW), device=dev).contiguous(memory_format=torch.channels_last)

@@ -35,6 +35,50 @@ def _nvcc() -> str:
     return exe
 
 
+EXT_SRC = os.path.join(CSRC, "torch_ext.cpp")
+EXT_PATH = os.path.join(CSRC, "lcr_torch.so")
+
+
+def ext_is_stale() -> bool:
+    if not os.path.exists(EXT_PATH):
+        return True
+    newest = max(os.path.getmtime(EXT_SRC), os.path.getmtime(os.path.join(INCLUDE, "lcr.h")))
+    return os.path.getmtime(EXT_PATH) < newest
+
+
+def build_torch_ext(force: bool = False, verbose: bool = False) -> str:
+    """g++ -> csrc/lcr_torch.so: the thin torch extension (C++ autograd node of RoIAlign, nms) over liblcr.so.
+    Plain g++ against the installed torch headers; links liblcr.so through an $ORIGIN rpath, in-tree."""
+    if not force and not ext_is_stale():
+        return EXT_PATH
+    import sysconfig
+
+    import torch
+    tdir = os.path.dirname(torch.__file__)
+    tlib = os.path.join(tdir, "lib")
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    defs = ["-DTORCH_EXTENSION_NAME=lcr_torch", "-DTORCH_API_INCLUDE_EXTENSION_H",
+            f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+    for name in ("COMPILER_TYPE", "STDLIB", "BUILD_ABI"):
+        val = getattr(torch._C, f"_PYBIND11_{name}", None)
+        if val is not None:
+            defs.append(f'-DPYBIND11_{name}="{val}"')
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-deprecated-declarations", *defs,
+           "-I", INCLUDE, "-isystem", os.path.join(tdir, "include"),
+           "-isystem", os.path.join(tdir, "include", "torch", "csrc", "api", "include"),
+           "-isystem", os.path.join(cuda_home, "include"), "-isystem", sysconfig.get_paths()["include"],
+           EXT_SRC, "-o", EXT_PATH + ".tmp",
+           "-L", tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
+           "-L", CSRC, "-l:liblcr.so", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"g++ failed for torch_ext.cpp:\n{res.stdout}\n{res.stderr}")
+    os.replace(EXT_PATH + ".tmp", EXT_PATH)
+    return EXT_PATH
+
+
 def _newest_input() -> float:
     paths = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "lcr.h")]
     return max(os.path.getmtime(p) for p in paths)
@@ -82,3 +126,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)
+    print(build_torch_ext(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

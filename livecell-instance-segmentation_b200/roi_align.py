@@ -16,7 +16,7 @@ from typing import Sequence, Union
 import torch
 from torch import nn
 
-from . import ops
+from . import _ext, _lib, ops
 
 
 def convert_boxes_to_roi_format(boxes: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -77,10 +77,17 @@ class _RoIAlignFn(torch.autograd.Function):
 def roi_align(input: torch.Tensor, boxes, output_size, spatial_scale: float = 1.0, sampling_ratio: int = -1,
               aligned: bool = False) -> torch.Tensor:
     """torchvision.ops.roi_align signature (TV:ops/roi_align.py:204-260)."""
-    rois = _as_rois(boxes)
     if isinstance(output_size, int):
         output_size = (output_size, output_size)
     sr = max(int(sampling_ratio), 0)  # torchvision: <= 0 means adaptive
+    if not input.is_cuda:
+        raise _lib.LcrError("liblcr ops need CUDA tensors: the region pipeline has no CPU fallback")
+    ext = _ext.load()
+    if ext is not None:  # C++ call path + C++ autograd node (csrc/torch_ext.cpp): same kernels, no Python plumbing
+        if isinstance(boxes, (list, tuple)):
+            return ext.roi_align_list(input, list(boxes), float(spatial_scale), output_size[0], output_size[1], sr, bool(aligned))
+        return ext.roi_align(input, boxes, float(spatial_scale), output_size[0], output_size[1], sr, bool(aligned))
+    rois = _as_rois(boxes)
     return _RoIAlignFn.apply(((float(spatial_scale),), rois, None, tuple(output_size), sr, bool(aligned)), input)
 
 
@@ -140,6 +147,11 @@ class MultiScaleRoIAlign(nn.Module):
 def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
     """torchvision.ops.nms drop-in (TV:ops/boxes.py:20-48): int64 indices of the kept boxes, sorted by
     decreasing score.  One host sync (the dense return type needs the count)."""
+    if not boxes.is_cuda:
+        raise _lib.LcrError("liblcr ops need CUDA tensors: the region pipeline has no CPU fallback")
+    ext = _ext.load()
+    if ext is not None:
+        return ext.nms(boxes, scores, float(iou_threshold))
     n = boxes.shape[0]
     if n == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)

@@ -84,3 +84,24 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 for pat in ("import oracle", "from oracle", "liblcr_oracle", "orc_"):
                     assert pat not in src, (f, pat)
+
+
+def test_torch_extension_builds_loads_and_rejects_cpu_tensors():
+    """csrc/lcr_torch.so (C++ autograd node of RoIAlign + nms over the C-ABI): builds with plain g++ against the
+    installed torch, links liblcr.so in-tree, and refuses CPU tensors like every other entry point."""
+    import torch
+    from livecell_instance_segmentation_b200 import _ext, build, roi_align as ra
+    from livecell_instance_segmentation_b200._lib import LcrError
+    ext = _ext.load()
+    assert ext is not None and os.path.dirname(build.EXT_PATH) == os.path.dirname(build.LIB_PATH)
+    assert ext.lcr_version() == 100
+    for name in ("roi_align", "roi_align_list", "nms"):
+        assert hasattr(ext, name)
+    with pytest.raises(RuntimeError):
+        ext.nms(torch.zeros(3, 4), torch.zeros(3), 0.5)
+    with pytest.raises(RuntimeError):
+        ext.roi_align(torch.zeros(1, 4, 8, 8), torch.zeros(2, 5), 0.25, 7, 7, 2, False)
+    with pytest.raises(LcrError):
+        ra.nms(torch.zeros(3, 4), torch.zeros(3), 0.5)
+    with pytest.raises(LcrError):
+        ra.roi_align(torch.zeros(1, 4, 8, 8), [torch.zeros(2, 4)], (7, 7), 0.25, 2)

@@ -18,6 +18,8 @@ LCR_ROI_FWD=cta LCR_ROI_BWD=cta LCR_PASTE=rows16 timeout 600 python -m pytest te
 echo "alt roi/paste (per-CTA RoIAlign, per-thread paste) rc=$?: $(tail -1 gpurun_out/test_alt_roi_paste.log)"
 LCR_NMS_RESOLVE=serial timeout 600 python -m pytest tests/test_gpu_nms.py tests/test_gpu_pipeline.py -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/test_alt_nms.log 2>&1
 echo "alt nms (serial chunk resolve) rc=$?: $(tail -1 gpurun_out/test_alt_nms.log)"
+LCR_TORCH_EXT=0 timeout 600 python -m pytest tests/test_gpu_roi_align.py tests/test_gpu_nms.py tests/test_gpu_pipeline.py -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/test_alt_ctypes.log 2>&1
+echo "alt call path (ctypes + Python autograd instead of csrc/lcr_torch.so) rc=$?: $(tail -1 gpurun_out/test_alt_ctypes.log)"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke rc=$?: $(tail -1 gpurun_out/smoke.log)"
 if [ "$1" != "--no-bench" ]; then

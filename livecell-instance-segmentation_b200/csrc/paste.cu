@@ -152,7 +152,7 @@ constexpr int kPasteRB = 11 * 1024;   // one row chunk (16 rows of a 704-px fram
 
 __global__ void __launch_bounds__(kPasteThreads) paste_bulk_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
                                                                    const uint8_t* __restrict__ valid, int N, int M, int H, int W,
-                                                                   float thr, uint32_t on_value, uint8_t* __restrict__ out, int zb_bytes) {
+                                                                   float thr, uint32_t on_value, uint8_t* __restrict__ out, int zb_bytes, int interleave) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint8_t* zb = smem;
   uint8_t* rb = smem + zb_bytes;                                               // two chunks of kPasteRB bytes
@@ -168,8 +168,11 @@ __global__ void __launch_bounds__(kPasteThreads) paste_bulk_kernel(const float* 
   const int MM = M * M;
   int buf = 0;
   // Bulk-group bookkeeping (thread 0): groups complete in commit order; a row chunk may be recomposed once the group
-  // that stored it has finished READING shared memory.  The zero-row stores of a frame are committed LAST, in their
-  // own group, so they never sit between a chunk and its reuse: the copy engine drains them in the background.
+  // that stored it has finished READING shared memory.  The SM's copy engine drains its queue in order, so the wait
+  // for a chunk only ends when everything queued before it has gone out — and the queue must not run dry meanwhile:
+  // the frame's zero rows (95 % of its bytes) are therefore not issued in one piece after the box rows, but as one
+  // slice (its own group) behind every chunk store, so there is always zero-row work queued BEHIND the chunk the
+  // CTA waits for next (r01c issued them last: the queue ran dry during every chunk wait, 11 % of the kernel).
   int seq = 0;                      // groups committed so far
   int last_use[2] = {-1, -1};       // group id of each chunk buffer's latest store
 
@@ -178,11 +181,32 @@ __global__ void __launch_bounds__(kPasteThreads) paste_bulk_kernel(const float* 
     const PasteBox pb = make_paste_box(boxes, det, M, H, W);
     uint8_t* frame = out + (size_t)det * H * W;
     const int y1 = pb.live ? pb.y1 : 0, y2 = pb.live ? pb.y2 : 0;
+    // zero rows [0, y1) and [y2, H) as one virtual byte range walked by a cursor (thread 0)
+    const size_t z_top = (size_t)y1 * W, z_all = z_top + (size_t)(H - y2) * W;
+    size_t z_cur = 0;
+    auto emit_zeros = [&](size_t upto) {  // thread 0: bulk stores from the zero buffer for virtual bytes [z_cur, upto), one group
+      upto = upto < z_all ? upto : z_all;
+      if (z_cur >= upto) return;
+      while (z_cur < upto) {
+        const bool top = z_cur < z_top;
+        const size_t seg_end = top ? (z_top < upto ? z_top : upto) : upto;
+        const size_t gaddr = top ? z_cur : (size_t)y2 * W + (z_cur - z_top);
+        const uint32_t n = (uint32_t)min((size_t)zb_bytes, seg_end - z_cur);
+        paste_bulk_store(frame + gaddr, zb, n, pol);
+        z_cur += n;
+      }
+      paste_bulk_commit();
+      ++seq;
+    };
     if (pb.live) {
       // the previous frame's readers of sprob passed the barrier that followed their last chunk
       const float* prob = probs + (size_t)det * MM;
       for (int i = tid; i < MM; i += kPasteThreads) sprob[i] = __ldg(prob + i);
-      for (int yc = y1; yc < y2; yc += chunk_rows) {
+      const int nchunks = (y2 - y1 + chunk_rows - 1) / chunk_rows;
+      // slice of the zero range issued behind each chunk (multiple of 16 B: W % 16 == 0 keeps every store aligned)
+      const size_t slice = ((z_all / (size_t)nchunks) + 15) & ~(size_t)15;
+      int ci = 0;
+      for (int yc = y1; yc < y2; yc += chunk_rows, ++ci) {
         const int rows = min(chunk_rows, y2 - yc);
         uint8_t* chunk = rb + buf * kPasteRB;
         if (tid == 0) {  // groups younger than this buffer's last store may stay pending
@@ -193,30 +217,28 @@ __global__ void __launch_bounds__(kPasteThreads) paste_bulk_kernel(const float* 
           else paste_bulk_wait_read<3>();
         }
         __syncthreads();                         // (also publishes sprob)
-        for (int r = warp; r < rows; r += kPasteThreads / 32) {
+        // Compose the chunk.  The box covers a few 16-pixel vectors of each row: the vectors outside it are zero-filled,
+        // and the 4-pixel words inside it are dealt round-robin to ALL threads (a lane = column mapping left the
+        // bilinear work to the handful of lanes whose columns fall into the box: 5-10 us per chunk, on the CTA's
+        // critical path between two bursts of stores).
+        const int vb0 = pb.x1 >> 4, vb1 = (pb.x2 + 15) >> 4;  // vectors [vb0, vb1) intersect the box
+        for (int i = tid; i < rows * vpr; i += kPasteThreads) {
+          const int r = i / vpr, xv = i - r * vpr;
+          if (xv < vb0 || xv >= vb1) *reinterpret_cast<uint4*>(chunk + (size_t)r * W + xv * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        const int nwb = (vb1 - vb0) * 4;  // words per row inside those vectors
+        for (int j = tid; j < rows * nwb; j += kPasteThreads) {
+          const int r = j / nwb, x0 = (vb0 << 4) + (j - r * nwb) * 4;
           int h0, h1;
           float wy0, wy1;
           src_index(pb.sh, yc + r - pb.y1, M, h0, h1, wy0, wy1);
-          for (int xv = lane; xv < vpr; xv += 32) {
-            const int x0 = xv * 16;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (x0 < pb.x2 && x0 + 16 > pb.x1) {
-              uint32_t w[4];
+          uint32_t word = 0u;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint32_t word = 0u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int x = x0 + q * 4 + j;
-                  if (x >= pb.x1 && x < pb.x2 && paste_pixel_smem(sprob, M, h0, h1, wy0, wy1, pb.sw, x - pb.x1, thr))
-                    word |= on_value << (8 * j);
-                }
-                w[q] = word;
-              }
-              v = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            *reinterpret_cast<uint4*>(chunk + (size_t)r * W + x0) = v;
+          for (int q = 0; q < 4; ++q) {
+            const int x = x0 + q;
+            if (x >= pb.x1 && x < pb.x2 && paste_pixel_smem(sprob, M, h0, h1, wy0, wy1, pb.sw, x - pb.x1, thr)) word |= on_value << (8 * q);
           }
+          *reinterpret_cast<uint32_t*>(chunk + (size_t)r * W + x0) = word;
         }
         paste_fence_async();
         __syncthreads();
@@ -224,23 +246,12 @@ __global__ void __launch_bounds__(kPasteThreads) paste_bulk_kernel(const float* 
           paste_bulk_store(frame + (size_t)yc * W, chunk, (uint32_t)(rows * W), pol);
           paste_bulk_commit();
           last_use[buf] = seq++;
+          if (interleave) emit_zeros(ci + 1 == nchunks ? z_all : z_cur + slice);
         }
         buf ^= 1;
       }
     }
-    if (tid == 0) {  // rows [0, y1) and [y2, H) are zeros: bulk stores straight from the zero buffer, one group
-      for (int part = 0; part < 2; ++part) {
-        size_t a = part == 0 ? 0 : (size_t)y2 * W;
-        const size_t b = part == 0 ? (size_t)y1 * W : (size_t)H * W;
-        while (a < b) {
-          const uint32_t n = (uint32_t)min((size_t)zb_bytes, b - a);
-          paste_bulk_store(frame + a, zb, n, pol);
-          a += n;
-        }
-      }
-      paste_bulk_commit();
-      ++seq;
-    }
+    if (tid == 0) emit_zeros(z_all);  // whatever is left (all of it for an empty box)
   }
   if (tid == 0) paste_bulk_wait_all();
 }
@@ -304,7 +315,8 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
     const long long max_blocks = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
     const int blocks = (int)((long long)N < max_blocks ? N : max_blocks);
     paste_bulk_kernel<<<blocks, kPasteThreads, bulk_smem, as_stream(stream)>>>(probs, boxes, valid, N, M, H, W, threshold,
-                                                                              (uint32_t)on_value, out, zb_bytes);
+                                                                              (uint32_t)on_value, out, zb_bytes,
+                                                                              (mode && strcmp(mode, "zeros_last") == 0) ? 0 : 1);
     return after_launch();
   }
   if (fast) {

@@ -124,6 +124,13 @@ def main():
             cy = cy.clamp(side / 2, B.IMG_H - side / 2)
             fx[:, 1], fx[:, 2], fx[:, 3], fx[:, 4] = cx - side / 2, cy - side / 2, cx + side / 2, cy + side / 2
             run(f"real centres, every box {int(side)}x{int(side)}", fx)
+        pad = r0.clone()
+        pad[:, 0] = -1.0
+        run("every RoI padding (zero tile + bulk store only: the store path alone)", pad)
+        tiny = r0.clone()
+        cx, cy = (r0[:, 1] + r0[:, 3]) / 2, (r0[:, 2] + r0[:, 4]) / 2
+        tiny[:, 1], tiny[:, 2], tiny[:, 3], tiny[:, 4] = cx, cy, cx + 2.0, cy + 2.0
+        run("real centres, every box 2x2 px (tables + row loop + store, 2x2-pixel windows)", tiny)
         # spatially sorted inside each frame (row-major 64-px cells): neighbours in the list overlap
         key = r0[:, 0] * 1e6 + torch.floor((r0[:, 2] + r0[:, 4]) / 128) * 1e3 + (r0[:, 1] + r0[:, 3]) / 2
         key = torch.where(live, key, torch.full_like(key, 1e12))
@@ -155,7 +162,7 @@ def main():
         boxes_flat = det.boxes.reshape(-1, 4)
         bytes_paste = n_det * (B.IMG_H * B.IMG_W + B.M * B.M * 4 + 16)
         ref = None
-        for name, env in [("rows16(r01)", {"LCR_PASTE": "rows16"}), ("bulk", {}), ("bulk,zb8", {"LCR_PASTE_ZB_KB": "8"}),
+        for name, env in [("rows16(r01)", {"LCR_PASTE": "rows16"}), ("bulk, zero rows last (r01c)", {"LCR_PASTE": "zeros_last"}), ("bulk", {}), ("bulk,zb8", {"LCR_PASTE_ZB_KB": "8"}),
                           ("bulk,zb32", {"LCR_PASTE_ZB_KB": "32"}), ("bulk,zb64", {"LCR_PASTE_ZB_KB": "64"})]:
             setenv(env)
             masks.fill_(7)
@@ -171,6 +178,10 @@ def main():
             emit(kernel="paste", variant=name, ms=med, ms_min=mn, GBps=bytes_paste / 1e9 / (med * 1e-3),
                  frac=bytes_paste / 1e9 / (med * 1e-3) / peak, identical_to_first=same, detections=n_det)
         setenv({})
+        dead = torch.zeros_like(boxes_flat)
+        med, mn = timed(lambda: ops.paste_masks(probs_d, dead, B.IMG_H, B.IMG_W, 0.5, 255, valid=det.valid, out=masks), args.reps)
+        emit(kernel="paste experiment", variant="every box empty (zero-buffer bulk stores only)", ms=med, ms_min=mn,
+             GBps=bytes_paste / 1e9 / (med * 1e-3), frac=bytes_paste / 1e9 / (med * 1e-3) / peak)
         med, mn = timed(lambda: masks.zero_(), args.reps)
         emit(kernel="reference: torch zero_() of the same 11.7 GB (pure HBM write stream)", ms=med, ms_min=mn,
              GBps=masks.numel() / 1e9 / (med * 1e-3), frac=masks.numel() / 1e9 / (med * 1e-3) / peak)

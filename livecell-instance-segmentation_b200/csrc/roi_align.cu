@@ -425,21 +425,24 @@ __device__ __forceinline__ int build_tables_warp(WarpTables<P>& tb, const RoiGeo
   }
   __syncwarp();
   int run = 0;
-  if (lane == 31) {  // row reuse flags: a sequential scan over <= 2P samples
-    int c0 = -1, c1 = -1;
-    for (int t = 0; t < 2 * P; ++t) {
-      const int lo = tb.lo[1][t], hi = tb.hi[1][t];
-      if (lo < 0) {
-        tb.ymode[t] = 0u;
-        continue;
+  {  // row reuse flags: sample t compares its rows with the previous VALID sample's (one ballot + two shuffles
+     // instead of a 2P-step serial scan on one lane, which was half of the table build's latency)
+    const int ylo = lane < 2 * P ? tb.lo[1][lane] : -1, yhi = lane < 2 * P ? tb.hi[1][lane] : 0;
+    const uint32_t before = __ballot_sync(0xffffffffu, ylo >= 0) & ((1u << lane) - 1u);
+    const int prev = before ? 31 - __clz(before) : lane;
+    int c0 = __shfl_sync(0xffffffffu, ylo, prev), c1 = __shfl_sync(0xffffffffu, yhi, prev);
+    if (!before) c0 = c1 = -1;
+    if (lane < 2 * P) {
+      uint32_t m = 0u;
+      if (ylo >= 0) {
+        m = (ylo == c0) ? kSame : ((ylo == c1) ? kShift : kNew);
+        if (yhi == ylo) m |= kBorder;
+        m |= kValid;
       }
-      uint32_t m = (lo == c0) ? kSame : ((lo == c1) ? kShift : kNew);
-      if (hi == lo) m |= kBorder;
-      tb.ymode[t] = m | kValid;
-      c0 = lo;
-      c1 = hi;
+      tb.ymode[lane] = m;
     }
-  } else if (lane < P) {  // fold the two samples of bin `lane` into weights over a run of columns
+  }
+  if (lane < P) {  // fold the two samples of bin `lane` into weights over a run of columns
     const int l0 = tb.lo[0][2 * lane], h0 = tb.hi[0][2 * lane];
     const int l1 = tb.lo[0][2 * lane + 1], h1 = tb.hi[0][2 * lane + 1];
     float* w = reinterpret_cast<float*>(&tb.xw[lane]);

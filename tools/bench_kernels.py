@@ -88,6 +88,12 @@ def main():
                           ("warp,ipw2,carveout75,prefetch.L1 dist2", {"LCR_ROI_CARVEOUT": "75", "LCR_ROI_PF": "1,2"}),
                           ("warp,ipw2,carveout75,dead-load dist2", {"LCR_ROI_CARVEOUT": "75", "LCR_ROI_PF": "2,2"}),
                           ("warp,ipw2,carveout50,prefetch.L1 dist2", {"LCR_ROI_CARVEOUT": "50", "LCR_ROI_PF": "1,2"}),
+                          ("warp,ipw2,carveout50", {"LCR_ROI_CARVEOUT": "50"}),
+                          ("warp,ipw2,carveout50,prefetch.L1 dist1", {"LCR_ROI_CARVEOUT": "50", "LCR_ROI_PF": "1,1"}),
+                          ("warp,ipw2,carveout50,dead-load dist1", {"LCR_ROI_CARVEOUT": "50", "LCR_ROI_PF": "2,1"}),
+                          ("warp,ipw2,carveout25", {"LCR_ROI_CARVEOUT": "25"}),
+                          ("warp,ipw2,carveout25,prefetch.L1 dist1", {"LCR_ROI_CARVEOUT": "25", "LCR_ROI_PF": "1,1"}),
+                          ("warp,ipw2,carveout25,dead-load dist1", {"LCR_ROI_CARVEOUT": "25", "LCR_ROI_PF": "2,1"}),
                           ("warp,ipw2 (default again)", {"LCR_ROI_CARVEOUT": "-1"})]:
             setenv(env)
             out = pipe.pool(feat, props.rois)

@@ -25,7 +25,6 @@
 //
 // Roofline: HBM.  Algorithmic bytes fwd = 4*K*C*P*P (out) + unique feature bytes + 20*K.
 // Generic kernels (any strides / sampling ratio / pooled size) back every other configuration.
-#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -528,32 +527,9 @@ __device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, int xb0, 
 
 // Walks the distinct rows of the window and writes this lane's two channels x 7 x-bins of the tile.
 // Every branch is warp-uniform and says so through a vote, so that ptxas keeps the uniform datapath.
-// L1 prefetch of the window rows a later sample will pool (pf.dist samples ahead): one instruction covers 16 columns
-// of a row (lane = column, half-warps take the two 128-byte lines of the item's 64 channels), so the demand loads
-// of that row hit L1 instead of paying an L2 round trip per row.  kind 1: prefetch.global.L1, kind 2: a load whose
-// result is never read.
-struct RowPrefetch {
-  const char* base;  // lane's address in row 0 of the map: item base + (col_lo + lane%16) columns + (lane/16) * 128 B
-  uint32_t step16;   // byte distance of 16 columns
-  int ncols;         // columns of the window still to cover from this lane's column on (<= 0: lane idle)
-  int dist;          // 0 = off
-  int kind;
-};
-__device__ __forceinline__ void prefetch_row(const RowPrefetch& pf, uint32_t row_off) {
-  const char* a = pf.base + row_off;
-  if (pf.kind == 1) {
-    if (pf.ncols > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-    if (pf.ncols > 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(a + pf.step16));
-  } else {
-    uint32_t d0, d1;
-    if (pf.ncols > 0) asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(d0) : "l"(a));
-    if (pf.ncols > 16) asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(d1) : "l"(a + pf.step16));
-  }
-}
-
 template <int P, int XB, int NB, int CSW>
 __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, int xb0, const char* __restrict__ fb, uint32_t swb,
-                                              float* __restrict__ my, const RowPrefetch pf) {
+                                              float* __restrict__ my) {
   constexpr int PP = P * P;
   constexpr uint32_t kAll = 0xffffffffu;
   float2 T0[XB], T1[XB], acc[XB];
@@ -578,14 +554,6 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, int xb0, 
 #pragma unroll 1
   for (int t = 0; t < 2 * P; ++t) {
     const uint32_t m = tb.ymode[t];
-    if (pf.dist > 0 && t + pf.dist < 2 * P) {  // warp-uniform
-      const uint32_t m2 = tb.ymode[t + pf.dist];
-      if (__any_sync(kAll, (m2 & kValid) && (m2 & kModeMask) != kSame)) {
-        const AxisTapB s2 = tb.ys[t + pf.dist];
-        if ((m2 & kModeMask) == kNew) prefetch_row(pf, s2.off_lo);
-        if (!(m2 & kBorder)) prefetch_row(pf, s2.off_hi);
-      }
-    }
     if (__any_sync(kAll, m & kValid)) {
       const uint32_t mode = m & kModeMask;
       const AxisTapB s = tb.ys[t];
@@ -741,21 +709,9 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
       // lanes past the last channel pair of a short group redo the last pair (their tile rows are not stored)
       const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)gb * lv.sn + c0 + min(2 * pair, nch - 2));  // sc == 1
       const uint32_t swb = (uint32_t)lv.sw * 4u;
-      RowPrefetch pf;
-      pf.dist = (nch == 64 && WI::kChannels == 64) ? (flags >> 4) & 7 : 0;  // full 64-channel items only (two whole lines per pixel)
-      pf.kind = (flags >> 2) & 3;
-      if (pf.dist > 0) {
-        const int c_lo = tb.xfirst[0];
-        const int c_hi = min(lv.W - 1, tb.xfirst[P - 1] + (run <= 4 ? max(run, 3) - 1 : tb.hi[0][2 * P - 1] - tb.xfirst[P - 1]));
-        const int col = c_lo + (lane & 15);
-        pf.ncols = c_hi - col + 1;
-        pf.step16 = 16u * swb;
-        pf.base = reinterpret_cast<const char*>(lv.data + (size_t)gb * lv.sn + c0) + (size_t)col * swb + (lane >> 4) * 128;
-        if (pf.kind == 0) pf.dist = 0;
-      }
-      if (__all_sync(kAll, run <= 3)) roi_warp_body<P, XB, 3, CSW>(tb, xb0, fb, swb, my, pf);
-      else if (__all_sync(kAll, run == 4)) roi_warp_body<P, XB, 4, CSW>(tb, xb0, fb, swb, my, pf);
-      else roi_warp_body<P, XB, 0, CSW>(tb, xb0, fb, swb, my, pf);
+      if (__all_sync(kAll, run <= 3)) roi_warp_body<P, XB, 3, CSW>(tb, xb0, fb, swb, my);
+      else if (__all_sync(kAll, run == 4)) roi_warp_body<P, XB, 4, CSW>(tb, xb0, fb, swb, my);
+      else roi_warp_body<P, XB, 0, CSW>(tb, xb0, fb, swb, my);
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -770,10 +726,7 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
   // Only the tile READS have to finish before the CTA's shared memory goes away; the writes complete on their own
   // before the grid does.  (wait_group without .read compiles to DEPBAR + CCTL.IVALL: every exiting CTA would
   // invalidate the SM's L1 under the three CTAs still gathering through it.)
-  if (lane == 0) {
-    if (flags & 128) bulk_wait_all();
-    else bulk_wait_read_all();
-  }
+  if (lane == 0) bulk_wait_read_all();
 }
 
 // ---- backward -----------------------------------------------------------------------------------
@@ -1271,17 +1224,7 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
     configured_dev = dev;
   }
   // flags: bit 0 = evict-first output stores, bit 1 = per-warp tables even when a RoI has exactly WARPS channel groups
-  // bits 2-3 = row prefetch kind (0 off, 1 prefetch.global.L1, 2 dead load), bits 4-6 = prefetch distance in samples
-  int flags = (env_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (env_is("LCR_ROI_SHARED_TABLES", "0") ? 2 : 0);
-  if (const char* v = getenv("LCR_ROI_PF")) {  // "kind,dist" — tuning switch
-    int kind = 0, dist = 1;
-    sscanf(v, "%d,%d", &kind, &dist);
-    flags |= (kind & 3) << 2 | (dist & 7) << 4;
-  }
-  if (env_is("LCR_ROI_EXIT_WAIT", "all")) flags |= 128;  // A/B: the r01c exit path
-  if (const char* v = getenv("LCR_ROI_CARVEOUT")) {  // tuning switch: shared-memory carve-out in percent (fewer CTAs, larger L1)
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v));
-  }
+  const int flags = (env_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (env_is("LCR_ROI_SHARED_TABLES", "0") ? 2 : 0);
   kern<<<blocks, WARPS * 32, smem, st>>>(p, out, groups, flags, ipw);
   return after_launch();
 }

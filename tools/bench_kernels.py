@@ -69,7 +69,7 @@ def main():
 
     def setenv(env):
         for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
-                  "LCR_ROI_PF", "LCR_ROI_CARVEOUT", "LCR_ROI_EXIT_WAIT", "LCR_NMS_RESOLVE"):
+                  "LCR_NMS_RESOLVE"):
             os.environ.pop(k, None)
         os.environ.update(env)
 
@@ -79,22 +79,7 @@ def main():
         for name, env in [("cta(r01)", {"LCR_ROI_FWD": "cta"}), ("warp,persistent", {"LCR_ROI_IPW": "0"}), ("warp,ipw1", {"LCR_ROI_IPW": "1"}),
                           ("warp,ipw2", {"LCR_ROI_IPW": "2"}), ("warp,ipw2,per-warp tables", {"LCR_ROI_IPW": "2", "LCR_ROI_SHARED_TABLES": "0"}),
                           ("warp,ipw3", {"LCR_ROI_IPW": "3"}), ("warp,ipw4", {"LCR_ROI_IPW": "4"}),
-                          ("warp,ipw2,exit wait_group (r01c)", {"LCR_ROI_EXIT_WAIT": "all"}),
-                          ("warp,ipw2,prefetch.L1 dist1", {"LCR_ROI_PF": "1,1"}), ("warp,ipw2,prefetch.L1 dist2", {"LCR_ROI_PF": "1,2"}),
-                          ("warp,ipw2,prefetch.L1 dist3", {"LCR_ROI_PF": "1,3"}),
-                          ("warp,ipw2,dead-load dist1", {"LCR_ROI_PF": "2,1"}), ("warp,ipw2,dead-load dist2", {"LCR_ROI_PF": "2,2"}),
-                          ("warp,ipw2,carveout75", {"LCR_ROI_CARVEOUT": "75"}),
-                          ("warp,ipw2,carveout75,prefetch.L1 dist1", {"LCR_ROI_CARVEOUT": "75", "LCR_ROI_PF": "1,1"}),
-                          ("warp,ipw2,carveout75,prefetch.L1 dist2", {"LCR_ROI_CARVEOUT": "75", "LCR_ROI_PF": "1,2"}),
-                          ("warp,ipw2,carveout75,dead-load dist2", {"LCR_ROI_CARVEOUT": "75", "LCR_ROI_PF": "2,2"}),
-                          ("warp,ipw2,carveout50,prefetch.L1 dist2", {"LCR_ROI_CARVEOUT": "50", "LCR_ROI_PF": "1,2"}),
-                          ("warp,ipw2,carveout50", {"LCR_ROI_CARVEOUT": "50"}),
-                          ("warp,ipw2,carveout50,prefetch.L1 dist1", {"LCR_ROI_CARVEOUT": "50", "LCR_ROI_PF": "1,1"}),
-                          ("warp,ipw2,carveout50,dead-load dist1", {"LCR_ROI_CARVEOUT": "50", "LCR_ROI_PF": "2,1"}),
-                          ("warp,ipw2,carveout25", {"LCR_ROI_CARVEOUT": "25"}),
-                          ("warp,ipw2,carveout25,prefetch.L1 dist1", {"LCR_ROI_CARVEOUT": "25", "LCR_ROI_PF": "1,1"}),
-                          ("warp,ipw2,carveout25,dead-load dist1", {"LCR_ROI_CARVEOUT": "25", "LCR_ROI_PF": "2,1"}),
-                          ("warp,ipw2 (default again)", {"LCR_ROI_CARVEOUT": "-1"})]:
+                          ("warp,ipw2 (again)", {})]:
             setenv(env)
             out = pipe.pool(feat, props.rois)
             torch.cuda.synchronize()

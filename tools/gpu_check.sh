@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 status=0
-for f in tests/test_gpu_match.py tests/test_gpu_boxes.py tests/test_gpu_select.py tests/test_gpu_nms.py tests/test_gpu_roi_align.py tests/test_gpu_paste.py tests/test_gpu_pipeline.py tests/test_gpu_guards.py tests/test_gpu_properties.py; do
+for f in tests/test_gpu_match.py tests/test_gpu_boxes.py tests/test_gpu_select.py tests/test_gpu_nms.py tests/test_gpu_roi_align.py tests/test_gpu_paste.py tests/test_gpu_pipeline.py tests/test_gpu_guards.py tests/test_gpu_properties.py tests/test_gpu_fuzz.py; do
   name=$(basename $f .py)
   timeout 600 python -m pytest $f -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/$name.log 2>&1
   rc=$?

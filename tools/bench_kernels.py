@@ -68,7 +68,7 @@ def main():
         print(json.dumps(kw), flush=True)
 
     def setenv(env):
-        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
+        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_PASTE_CTAS", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
                   "LCR_NMS_RESOLVE"):
             os.environ.pop(k, None)
         os.environ.update(env)
@@ -177,6 +177,44 @@ def main():
         emit(kernel="reference: torch zero_() of the same 11.7 GB (pure HBM write stream)", ms=med, ms_min=mn,
              GBps=masks.numel() / 1e9 / (med * 1e-3), frac=masks.numel() / 1e9 / (med * 1e-3) / peak)
         del masks
+
+    if "overlap" in only:
+        # RoIAlign (L1/latency-bound) and paste (HBM-write-bound) side by side on two streams vs back to back
+        masks = torch.empty((F * B.MAX_DET, B.IMG_H, B.IMG_W), dtype=torch.uint8, device=dev)
+        boxes_flat = det.boxes.reshape(-1, 4)
+        roi_out = torch.empty((F * B.POST_NMS, B.C, 7, 7), device=dev)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def roi():
+            ops.roi_align_fwd([feat], [0.25], props.rois, None, (7, 7), 2, False, out=roi_out)
+
+        def paste():
+            ops.paste_masks(probs_d, boxes_flat, B.IMG_H, B.IMG_W, 0.5, 255, valid=det.valid, out=masks)
+
+        def seq():
+            roi()
+            paste()
+
+        def par():
+            cur = torch.cuda.current_stream()
+            s1.wait_stream(cur)
+            s2.wait_stream(cur)
+            with torch.cuda.stream(s2):
+                paste()
+            with torch.cuda.stream(s1):
+                roi()
+            cur.wait_stream(s1)
+            cur.wait_stream(s2)
+
+        med, mn = timed(seq, args.reps, flush)
+        emit(kernel="roi_align_fwd + paste", variant="back to back, one stream", ms=med, ms_min=mn)
+        for cap in ("5", "4", "3", "2", "1"):
+            setenv({"LCR_PASTE_CTAS": cap})
+            med_p, _ = timed(paste, args.reps)
+            med, mn = timed(par, args.reps, flush)
+            emit(kernel="roi_align_fwd || paste", variant=f"two streams, paste capped at {cap} CTAs/SM", ms=med, ms_min=mn, paste_alone_ms=med_p)
+        setenv({})
+        del masks, roi_out
 
     if "select" in only:
         bytes_sel = F * (4 * B.A * B.FH * B.FW) + F * B.PRE_NMS * 28

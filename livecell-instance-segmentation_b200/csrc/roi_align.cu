@@ -485,7 +485,8 @@ __device__ __forceinline__ float2 ldg_f2b(const char* p) { return __ldg(reinterp
 // CSW: compile-time column stride in elements (0 = use swb).
 template <int P, int XB, int NB, int CSW>
 __device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, int xb0, const uint32_t (&xo)[XB],
-                                              const char* __restrict__ row, uint32_t swb, float2 (&T)[XB]) {
+                                              const float (&xw)[XB][NB > 0 ? NB : 1], const char* __restrict__ row, uint32_t swb,
+                                              float2 (&T)[XB]) {
   const uint32_t cs = CSW ? (uint32_t)CSW * 4u : swb;
   if (NB > 0) {
     float2 v[XB][NB > 0 ? NB : 1];
@@ -497,11 +498,9 @@ __device__ __forceinline__ void pool_row_warp(const WarpTables<P>& tb, int xb0, 
     }
 #pragma unroll
     for (int pw = 0; pw < XB; ++pw) {
-      const float4 w = tb.xw[xb0 + pw];
-      float2 t = __fmul2_rn(splat(w.x), v[pw][0]);
-      t = ffma2(splat(w.y), v[pw][1], t);
-      if (NB > 2) t = ffma2(splat(w.z), v[pw][2], t);
-      if (NB > 3) t = ffma2(splat(w.w), v[pw][3], t);
+      float2 t = __fmul2_rn(splat(xw[pw][0]), v[pw][0]);
+#pragma unroll
+      for (int j = 1; j < NB; ++j) t = ffma2(splat(xw[pw][j]), v[pw][j], t);
       T[pw] = t;
     }
   } else {
@@ -539,6 +538,17 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, int xb0, 
     T0[pw] = T1[pw] = acc[pw] = make_float2(0.f, 0.f);
     xo[pw] = NB > 0 ? tb.xoff[xb0 + pw] : 0u;
   }
+  // the bins' folded column weights stay in registers for the whole RoI (one broadcast LDS.128 per bin per ROW before:
+  // 105 of the item's 375 shared-memory wavefronts, on the LSU data pipe that bounds the kernel)
+  float xw[XB][NB > 0 ? NB : 1];
+#pragma unroll
+  for (int pw = 0; pw < XB; ++pw) {
+    const float4 w = tb.xw[xb0 + pw];
+    xw[pw][0] = w.x;
+    if (NB > 1) xw[pw][1 % (NB > 0 ? NB : 1)] = w.y;
+    if (NB > 2) xw[pw][2 % (NB > 0 ? NB : 1)] = w.z;
+    if (NB > 3) xw[pw][3 % (NB > 0 ? NB : 1)] = w.w;
+  }
   // P = 7, tile stores without bank conflicts: the lane's channel rows start 98 words apart, so lanes l and
   // l+16 share banks; the upper half-warp therefore stores its odd channel while the lower stores its even
   // one (49 words = 17 banks apart) and vice versa.  (P = 14: plain order.)
@@ -563,7 +573,7 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, int xb0, 
       const bool border = __any_sync(kAll, m & kBorder);
       const bool is_new = __any_sync(kAll, mode == kNew), is_shift = __any_sync(kAll, mode == kShift);
       auto y_step = [&](auto& LO, auto& HI) -> bool {  // returns true when the sets swapped roles
-        if (is_new || (is_shift && !border)) pool_row_warp<P, XB, NB, CSW>(tb, xb0, xo, fb + (is_new ? s.off_lo : s.off_hi), swb, LO);
+        if (is_new || (is_shift && !border)) pool_row_warp<P, XB, NB, CSW>(tb, xb0, xo, xw, fb + (is_new ? s.off_lo : s.off_hi), swb, LO);
         if (is_shift && !border) {  // lower row = HI (kept), upper row = LO (just pooled)
 #pragma unroll
           for (int pw = 0; pw < XB; ++pw) {
@@ -580,7 +590,7 @@ __device__ __forceinline__ void roi_warp_body(const WarpTables<P>& tb, int xb0, 
 #pragma unroll
             for (int pw = 0; pw < XB; ++pw) HI[pw] = LO[pw];
           } else {
-            pool_row_warp<P, XB, NB, CSW>(tb, xb0, xo, fb + s.off_hi, swb, HI);
+            pool_row_warp<P, XB, NB, CSW>(tb, xb0, xo, xw, fb + s.off_hi, swb, HI);
           }
         }
 #pragma unroll

@@ -256,6 +256,110 @@ __global__ void __launch_bounds__(kPasteThreads) paste_bulk_kernel(const float* 
   if (tid == 0) paste_bulk_wait_all();
 }
 
+// ---- TMA path, warp-specialised (default) -----------------------------------------------------------
+// Same stores as paste_bulk_kernel, but issued by two independent roles of a persistent CTA (160 threads):
+//   * warp 0, lane 0 — the ZERO ISSUER: walks the CTA's detections and hands the copy engine the zero rows of every
+//     frame (95 % of the bytes), never waiting for anything but the engine's own back-pressure;
+//   * warps 1-4 — the COMPOSERS: stage the detection's probabilities, compose the box rows (bilinear + threshold,
+//     box words dealt round-robin to the 128 threads) into a ring of kSlots row chunks and store them; their bulk
+//     groups belong to composer thread 0, which only waits when a ring slot comes round again (kSlots chunks later).
+// The two roles write disjoint bytes and never synchronise with each other (composers use a named barrier), so the
+// HBM write stream no longer pauses while a CTA composes — the r01d single-role kernel left ~7 % on the table
+// against its all-empty-boxes floor.
+constexpr int kSplitThreads = 160;
+constexpr int kComposers = 128;
+constexpr int kSlots = 8;
+
+__device__ __forceinline__ void composer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kComposers) : "memory"); }
+
+__global__ void __launch_bounds__(kSplitThreads) paste_split_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
+                                                                    const uint8_t* __restrict__ valid, int N, int M, int H, int W,
+                                                                    float thr, uint32_t on_value, uint8_t* __restrict__ out, int zb_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint8_t* zb = smem;
+  uint8_t* rb = smem + zb_bytes;                                                   // kSlots chunks of kPasteRB bytes
+  float* sprob = reinterpret_cast<float*>(smem + zb_bytes + kSlots * kPasteRB);   // [M*M]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < zb_bytes / 16; i += kSplitThreads) reinterpret_cast<uint4*>(zb)[i] = make_uint4(0u, 0u, 0u, 0u);
+  paste_fence_async();
+  __syncthreads();
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+
+  if (tid < 32) {
+    // ---- zero issuer --------------------------------------------------------------------------
+    if (tid != 0) return;
+    for (int det = blockIdx.x; det < N; det += gridDim.x) {
+      if (valid && !valid[det]) continue;
+      const PasteBox pb = make_paste_box(boxes, det, M, H, W);
+      uint8_t* frame = out + (size_t)det * H * W;
+      const int y1 = pb.live ? pb.y1 : 0, y2 = pb.live ? pb.y2 : 0;
+      for (int part = 0; part < 2; ++part) {
+        size_t a = part == 0 ? 0 : (size_t)y2 * W;
+        const size_t b = part == 0 ? (size_t)y1 * W : (size_t)H * W;
+        while (a < b) {
+          const uint32_t n = (uint32_t)min((size_t)zb_bytes, b - a);
+          paste_bulk_store(frame + a, zb, n, pol);
+          a += n;
+        }
+      }
+      paste_bulk_commit();
+    }
+    paste_bulk_wait_read<0>();  // the zero buffer must outlive its readers
+    return;
+  }
+
+  // ---- composers ----------------------------------------------------------------------------------
+  const int ct = tid - 32;  // 0..127
+  const int vpr = W / 16;
+  const int chunk_rows = max(1, min(kPasteRB / W, H));
+  const int MM = M * M;
+  int slot = 0;
+  for (int det = blockIdx.x; det < N; det += gridDim.x) {
+    if (valid && !valid[det]) continue;  // uniform over the composers
+    const PasteBox pb = make_paste_box(boxes, det, M, H, W);
+    if (!pb.live) continue;
+    uint8_t* frame = out + (size_t)det * H * W;
+    const float* prob = probs + (size_t)det * MM;
+    composer_barrier();  // the previous detection's readers of sprob are done
+    for (int i = ct; i < MM; i += kComposers) sprob[i] = __ldg(prob + i);
+    const int vb0 = pb.x1 >> 4, vb1 = (pb.x2 + 15) >> 4;  // vectors [vb0, vb1) intersect the box
+    const int nwb = (vb1 - vb0) * 4;                       // words per row inside those vectors
+    for (int yc = pb.y1; yc < pb.y2; yc += chunk_rows) {
+      const int rows = min(chunk_rows, pb.y2 - yc);
+      uint8_t* chunk = rb + slot * kPasteRB;
+      // the slot's previous store (kSlots groups ago) must have finished reading it: at most kSlots - 1 younger groups pending
+      if (ct == 0) paste_bulk_wait_read<kSlots - 1>();
+      composer_barrier();  // (also publishes sprob)
+      for (int i = ct; i < rows * vpr; i += kComposers) {
+        const int r = i / vpr, xv = i - r * vpr;
+        if (xv < vb0 || xv >= vb1) *reinterpret_cast<uint4*>(chunk + (size_t)r * W + xv * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      for (int j = ct; j < rows * nwb; j += kComposers) {
+        const int r = j / nwb, x0 = (vb0 << 4) + (j - r * nwb) * 4;
+        int h0, h1;
+        float wy0, wy1;
+        src_index(pb.sh, yc + r - pb.y1, M, h0, h1, wy0, wy1);
+        uint32_t word = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int x = x0 + q;
+          if (x >= pb.x1 && x < pb.x2 && paste_pixel_smem(sprob, M, h0, h1, wy0, wy1, pb.sw, x - pb.x1, thr)) word |= on_value << (8 * q);
+        }
+        *reinterpret_cast<uint32_t*>(chunk + (size_t)r * W + x0) = word;
+      }
+      paste_fence_async();
+      composer_barrier();
+      if (ct == 0) {
+        paste_bulk_store(frame + (size_t)yc * W, chunk, (uint32_t)(rows * W), pol);
+        paste_bulk_commit();
+      }
+      slot = slot + 1 == kSlots ? 0 : slot + 1;
+    }
+  }
+  if (ct == 0) paste_bulk_wait_read<0>();
+}
+
 // Generic path (any W / alignment): one thread per pixel, byte stores.  Correctness path for odd
 // frame widths (e.g. the reference's 300x222 tiles are fine: 300 % 4 == 0 but 300 % 16 != 0).
 __global__ void __launch_bounds__(256) paste_generic_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
@@ -299,8 +403,35 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
   int zb_bytes = kPasteZB;
   if (const char* v = getenv("LCR_PASTE_ZB_KB")) zb_bytes = atoi(v) * 1024;   // tuning switch
   if (zb_bytes < 1024 || zb_bytes > 128 * 1024 || zb_bytes % 1024) zb_bytes = kPasteZB;
-  const size_t bulk_smem = (size_t)zb_bytes + 2 * kPasteRB + round_up(sizeof(float) * (size_t)M * M, 16);
-  if (fast && W <= kPasteRB && bulk_smem <= 200 * 1024 && !(mode && strcmp(mode, "rows16") == 0)) {
+  const size_t prob_bytes = round_up(sizeof(float) * (size_t)M * M, 16);
+  const bool want_rows16 = mode && strcmp(mode, "rows16") == 0;
+  const bool want_single = mode && (strcmp(mode, "single") == 0 || strcmp(mode, "zeros_last") == 0);  // the r01d single-role kernel
+  const size_t split_smem = (size_t)zb_bytes + (size_t)kSlots * kPasteRB + prob_bytes;
+  if (fast && W <= kPasteRB && split_smem <= 200 * 1024 && !want_rows16 && !want_single) {
+    static thread_local int configured_dev = -1;
+    static thread_local size_t configured_smem = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev || configured_smem < split_smem) {
+      cudaError_t e = cudaFuncSetAttribute(paste_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem);
+      if (e != cudaSuccess) return cuda_status(e);
+      configured_dev = dev;
+      configured_smem = split_smem;
+    }
+    // One persistent CTA per SM is enough for the zero issuer to keep the copy engine saturated (1.945 ms; 2 per SM: 1.959)
+    // and leaves 120 KB of shared memory per SM to a kernel running beside paste on another stream.
+    int per_sm = (int)((227 * 1024) / (split_smem + 1024));
+    int cap = 1;
+    if (const char* v = getenv("LCR_PASTE_CTAS")) cap = atoi(v);  // tuning switch
+    if (cap >= 1 && cap < per_sm) per_sm = cap;
+    const long long max_blocks = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
+    const int blocks = (int)((long long)N < max_blocks ? N : max_blocks);
+    paste_split_kernel<<<blocks, kSplitThreads, split_smem, as_stream(stream)>>>(probs, boxes, valid, N, M, H, W, threshold,
+                                                                                (uint32_t)on_value, out, zb_bytes);
+    return after_launch();
+  }
+  const size_t bulk_smem = (size_t)zb_bytes + 2 * kPasteRB + prob_bytes;
+  if (fast && W <= kPasteRB && bulk_smem <= 200 * 1024 && !want_rows16) {
     static thread_local int configured_dev = -1;
     static thread_local size_t configured_smem = 0;
     int dev = 0;

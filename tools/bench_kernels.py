@@ -153,7 +153,8 @@ def main():
         boxes_flat = det.boxes.reshape(-1, 4)
         bytes_paste = n_det * (B.IMG_H * B.IMG_W + B.M * B.M * 4 + 16)
         ref = None
-        for name, env in [("rows16(r01)", {"LCR_PASTE": "rows16"}), ("bulk, zero rows last (r01c)", {"LCR_PASTE": "zeros_last"}), ("bulk", {}), ("bulk,zb8", {"LCR_PASTE_ZB_KB": "8"}),
+        for name, env in [("rows16(r01)", {"LCR_PASTE": "rows16"}), ("bulk, zero rows last (r01c)", {"LCR_PASTE": "zeros_last"}), ("bulk, single role (r01d)", {"LCR_PASTE": "single"}), ("bulk, warp-specialised", {}),
+                          ("bulk, warp-specialised, 2 CTAs/SM", {"LCR_PASTE_CTAS": "2"}), ("bulk,zb8", {"LCR_PASTE_ZB_KB": "8"}),
                           ("bulk,zb32", {"LCR_PASTE_ZB_KB": "32"}), ("bulk,zb64", {"LCR_PASTE_ZB_KB": "64"})]:
             setenv(env)
             masks.fill_(7)

@@ -403,8 +403,8 @@ def run_ours(args):
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("frames_per_gpu") == F and n_det == F * MAX_DET:
-            traffic = tj["paste_bulk_kernel"]["dram_bytes_per_launch"]
-    roofline = {"kernel": "paste_bulk_kernel", "bound": "hbm", "achieved": paste_bytes / 1e9 / (paste_ms * 1e-3), "peak": peak,
+            traffic = tj.get("paste_split_kernel", {}).get("dram_bytes_per_launch")
+    roofline = {"kernel": "paste_split_kernel", "bound": "hbm", "achieved": paste_bytes / 1e9 / (paste_ms * 1e-3), "peak": peak,
                 "unit": "GB/s", "frac": paste_bytes / 1e9 / (paste_ms * 1e-3) / peak, "traffic": traffic,
                 "traffic_source": "profiles/ncu_traffic.json (ncu --set full, same workload)" if traffic else None,
                 "peak_source": peak_src, "bytes_per_launch": paste_bytes, "ms_per_launch": paste_ms,

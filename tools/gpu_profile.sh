@@ -7,7 +7,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 echo "launch list rc=$?"
 # one whole timed step of the region kernels (8 matching launches per step; skip the 3 warm-up steps)
 ncu --set full --clock-control none --import-source on \
-    -k regex:"roi_fwd_warp|paste_bulk|rpn_prefilter|rpn_sortfilter|nms_resolve|nms_mask|nms_jacobi" -s 24 -c 8 \
+    -k regex:"roi_fwd_warp|paste_split|paste_bulk|rpn_prefilter|rpn_sortfilter|nms_resolve|nms_mask|nms_jacobi" -s 24 -c 8 \
     -f -o gpurun_out/prof_full $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out/

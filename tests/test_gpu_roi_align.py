@@ -122,11 +122,14 @@ def test_multiscale_golden(golden, synth):
     assert_close_rel(N(out2), g["ms_out"], RTOL)
 
 
-def test_layout_helpers(ops, synth):
+@pytest.mark.parametrize("shape", [(2, 37, 19, 23), (3, 256, 33, 44), (2, 72, 10, 70), (1, 4, 2, 2), (2, 128, 64, 64)])
+def test_layout_helpers(ops, synth, shape):
+    """both transpose kernels: odd shapes (4-byte path) and C, H*W multiples of 4 (16-byte path, partial 64x64 tiles)"""
     from gpu_util import N, T
-    x = synth.make_features(2, 37, 19, 23, seed=3)
+    n, c, h, w = shape
+    x = synth.make_features(n, c, h, w, seed=3)
     y = ops.to_nhwc(T(x))
-    assert y.stride() == (19 * 23 * 37, 1, 23 * 37, 37)
+    assert y.stride() == (h * w * c, 1, w * c, c)
     assert np.array_equal(N(y), x)
     z = ops.to_nchw(y)
     assert z.is_contiguous() and np.array_equal(N(z), x)

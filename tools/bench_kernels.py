@@ -42,7 +42,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--only", default="roi,paste,select,nms,bwd")
+    ap.add_argument("--only", default="roi,paste,select,nms,bwd,layout")
     args = ap.parse_args()
     only = set(args.only.split(","))
     import torch
@@ -216,6 +216,15 @@ def main():
             emit(kernel="roi_align_fwd || paste", variant=f"two streams, paste capped at {cap} CTAs/SM", ms=med, ms_min=mn, paste_alone_ms=med_p)
         setenv({})
         del masks, roi_out
+
+    if "layout" in only:
+        # cost of an NCHW backbone: one tiled transpose of the level-0 maps before RoIAlign (channels_last models skip it)
+        nchw = feat.contiguous()
+        bytes_t = 2 * nchw.numel() * 4
+        med, mn = timed(lambda: ops.to_nhwc(nchw), args.reps, flush)
+        emit(kernel="nchw_to_nhwc (64 x 256 x 130 x 176)", variant="tiled transpose", ms=med, ms_min=mn, GBps=bytes_t / 1e9 / (med * 1e-3),
+             frac=bytes_t / 1e9 / (med * 1e-3) / peak)
+        del nchw
 
     if "select" in only:
         bytes_sel = F * (4 * B.A * B.FH * B.FW) + F * B.PRE_NMS * 28

@@ -299,6 +299,84 @@ __device__ __forceinline__ bool fast_path_done(const SelParams& p, int seg) {
   return p.pre_count && p.pre_count[2 * seg] <= (uint32_t)kPreCap && p.pre_count[2 * seg + 1] == 0u;
 }
 
+// Block-wide bitonic sort (descending) of SZ 64-bit keys in shared memory, SZ a power of two in [32, 8 * kSortThreads].
+// Thread t owns the E consecutive keys t*E .. t*E+E-1 in REGISTERS: compare-exchange passes with stride < E are register
+// swaps, strides < 32*E are warp shuffles, and only the strides that cross warps go through shared memory behind a
+// __syncthreads (15 of the 78 passes of a 4096-key sort).  The all-shared-memory version spent 3/4 of the kernel waiting
+// on LDS -> compare -> STS chains (ncu r01d source page).
+template <int E>
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* s, int SZ, int tid) {
+  const int lane = tid & 31;
+  const int base = tid * E;
+  const bool active = base < SZ;
+  unsigned long long k[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) k[r] = active ? s[base + r] : 0ull;
+  bool in_smem = false;  // uniform: where the current keys live
+  for (int size = 2; size <= SZ; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32 * E) {  // pairs in different warps
+        if (!in_smem) {
+          if (active) {
+#pragma unroll
+            for (int r = 0; r < E; ++r) s[base + r] = k[r];
+          }
+          in_smem = true;
+        }
+        __syncthreads();
+        for (int t = tid; t < (SZ >> 1); t += kSortThreads) {
+          const int i = 2 * t - (t & (stride - 1));
+          const int j = i + stride;
+          const unsigned long long x = s[i], y = s[j];
+          if ((x < y) == ((i & size) == 0)) {
+            s[i] = y;
+            s[j] = x;
+          }
+        }
+      } else {
+        if (in_smem) {
+          __syncthreads();
+#pragma unroll
+          for (int r = 0; r < E; ++r) k[r] = active ? s[base + r] : 0ull;
+          in_smem = false;
+        }
+        if (stride >= E) {  // partner key sits in another lane of this warp
+          const int lm = stride / E;
+          const bool lower = (lane & lm) == 0;
+#pragma unroll
+          for (int r = 0; r < E; ++r) {
+            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, k[r], lm);
+            const bool desc = ((base + r) & size) == 0;
+            const unsigned long long hi = k[r] > o ? k[r] : o, lo = k[r] > o ? o : k[r];
+            k[r] = (lower == desc) ? hi : lo;  // descending block: the lower index keeps the larger key
+          }
+        } else {  // both keys in this thread (static register indices: one unrolled body per possible stride)
+#pragma unroll
+          for (int ls = E >> 1; ls > 0; ls >>= 1) {
+            if (stride == ls) {
+#pragma unroll
+              for (int r = 0; r < E; ++r) {
+                if ((r & ls) == 0) {
+                  const bool desc = ((base + r) & size) == 0;
+                  const unsigned long long x = k[r], y = k[r + ls];
+                  if ((x < y) == desc) {
+                    k[r] = y;
+                    k[r + ls] = x;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!in_smem && active) {
+#pragma unroll
+    for (int r = 0; r < E; ++r) s[base + r] = k[r];
+  }
+}
+
 __global__ void __launch_bounds__(kSortThreads) rpn_sortfilter_kernel(const __grid_constant__ SelParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned long long* s = reinterpret_cast<unsigned long long*>(smem);
@@ -314,22 +392,12 @@ __global__ void __launch_bounds__(kSortThreads) rpn_sortfilter_kernel(const __gr
   while (SZ < M) SZ <<= 1;
   const unsigned long long* cand = p.pre_cand + (size_t)seg * kPreCap;
   for (int i = tid; i < SZ; i += kSortThreads) s[i] = i < M ? __ldcg(cand + i) : 0ull;  // 0 sorts last
-  // bitonic sort, descending
-  for (int size = 2; size <= SZ; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (int t = tid; t < (SZ >> 1); t += kSortThreads) {
-        const int i = 2 * t - (t & (stride - 1));
-        const int j = i + stride;
-        const unsigned long long x = s[i], y = s[j];
-        const bool desc = (i & size) == 0;
-        if ((x < y) == desc) {
-          s[i] = y;
-          s[j] = x;
-        }
-      }
-    }
-  }
+  __syncthreads();
+  const int epl = SZ / kSortThreads;  // keys per thread in the register phases (1 when the array is shorter than the CTA)
+  if (epl <= 1) bitonic_sort_desc<1>(s, SZ, tid);
+  else if (epl == 2) bitonic_sort_desc<2>(s, SZ, tid);
+  else if (epl == 4) bitonic_sort_desc<4>(s, SZ, tid);
+  else bitonic_sort_desc<8>(s, SZ, tid);
   __syncthreads();
   ordered_epilogue<kSortThreads, true>(p, seg, b, l, s, min(M, min(p.k, n)), s_warp);
 }

@@ -177,7 +177,7 @@ int lcr_level_map_f32(const float* boxes, int box_stride, int K, int k_min, int 
  * and, with L > 1 and roi_level given, MultiScaleRoIAlign (TV:ops/poolers.py:147-227).
  *
  * Each level is a [N, C, H, W] fp32 tensor addressed through ELEMENT strides, so both NCHW and
- * channels_last (NHWC memory) maps are accepted.  The TMA-staged fast path needs sc == 1 (NHWC),
+ * channels_last (NHWC memory) maps are accepted.  The warp-item fast path (TMA bulk store of the pooled tile) needs sc == 1 (NHWC),
  * C % 64 == 0 and 16-byte aligned rows; every other layout runs the generic kernel.
  * rois [K,5] = (batch_idx as float, x1, y1, x2, y2) (TV:ops/_utils.py:18-25).  A roi with
  * batch_idx < 0 is padding: forward writes zeros for it, backward ignores it.

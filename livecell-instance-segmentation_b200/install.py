@@ -76,25 +76,46 @@ def mask_head_probs(mask_head, roi_features):
     return ops.mask_tail(logits, int(logits.shape[-1]), 1)
 
 
+_ORIGINALS: list = []   # (owner object, attribute, original value) of everything install() replaced, in order
+
+
+def _swap(owner, attr, obj):
+    _ORIGINALS.append((owner, attr, getattr(owner, attr)))
+    setattr(owner, attr, obj)
+
+
+def uninstall() -> int:
+    """Undo every install() since the last uninstall(): the reference modules get their own callables back
+    (models constructed while installed keep their B200 RoIAlign module).  Returns the number of names restored."""
+    n = len(_ORIGINALS)
+    while _ORIGINALS:
+        owner, attr, orig = _ORIGINALS.pop()
+        setattr(owner, attr, orig)
+    return n
+
+
 def install(import_missing: bool = True) -> dict:
     """Patch every reference module that is (or can be) imported.  Returns {module: [patched names]}."""
     done = {}
-    for mod_name, repl in PATCHES.items():
-        names = [mod_name] + [a for a, target in ALIASES.items() if target == mod_name]
-        for name in names:
+    targets = []                       # resolve (import) every module first, so that each one still binds the reference's own
+    for mod_name, repl in PATCHES.items():   # callables when it is patched and uninstall() can give them back
+        for name in [mod_name] + [a for a, target in ALIASES.items() if target == mod_name]:
             mod = sys.modules.get(name)
             if mod is None and import_missing:
                 try:
                     mod = importlib.import_module(name)
                 except Exception:
                     mod = None
-            if not isinstance(mod, types.ModuleType):
-                continue
-            for attr, obj in repl.items():
-                if hasattr(mod, attr):
-                    setattr(mod, attr, obj)
-                    done.setdefault(name, []).append(attr)
-            if name.endswith("custom_maskrcnn") and hasattr(mod, "CustomMaskRCNN"):
-                mod.CustomMaskRCNN._generate_masks = _paste_method
-                done[name].append("CustomMaskRCNN._generate_masks")
+            if isinstance(mod, types.ModuleType):
+                targets.append((name, mod, repl))
+    for name, mod, repl in targets:
+        for attr, obj in repl.items():
+            if hasattr(mod, attr):
+                if getattr(mod, attr) is not obj:
+                    _swap(mod, attr, obj)
+                done.setdefault(name, []).append(attr)
+        if name.endswith("custom_maskrcnn") and hasattr(mod, "CustomMaskRCNN"):
+            if mod.CustomMaskRCNN._generate_masks is not _paste_method:
+                _swap(mod.CustomMaskRCNN, "_generate_masks", _paste_method)
+            done.setdefault(name, []).append("CustomMaskRCNN._generate_masks")
     return done

@@ -71,6 +71,12 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
+def _round_f32(x: float) -> float:
+    """x rounded to the nearest fp32, as a Python float."""
+    import struct
+    return struct.unpack("f", struct.pack("f", float(x)))[0]
+
+
 def base_anchors(sizes=(32, 64, 128), aspect_ratios=(0.5, 1.0, 2.0)):
     """Base anchors in float64 then fp32 — src/components/anchor_generator.py:15-27."""
     rows = []
@@ -204,10 +210,18 @@ def rpn_select(objectness: Sequence[torch.Tensor], *, k: int, img_size, score_th
 
 def nms_batched(boxes: torch.Tensor, scores: Optional[torch.Tensor], iou_threshold: float, *, post_n: int,
                 counts: Optional[torch.Tensor] = None, score_thresh: Optional[float] = None,
-                category: Optional[torch.Tensor] = None):
+                category: Optional[torch.Tensor] = None, cpu_threshold: bool = False):
     """a8 — greedy NMS over S segments: boxes [S, stride, 4]; scores [S, stride] or None (already
     sorted); counts [S] i32 or None.  Returns keep [S, post_n] i64 (original in-segment indices, score
-    order) and keep_counts [S] i32."""
+    order) and keep_counts [S] i32.
+
+    Threshold semantics (they differ only for a pair whose fp32 IoU equals float32(thr) exactly): torchvision's CUDA op
+    — what the reference executes on a GPU — compares the fp32 IoU with the threshold ROUNDED TO fp32; its CPU op
+    compares with the double.  The C-ABI takes a double and implements the CPU rule, so the CUDA rule is obtained by
+    pre-rounding the threshold here (default); cpu_threshold=True passes the double through (the CPU-generated golden
+    vectors and the oracle follow that rule)."""
+    if not cpu_threshold:
+        iou_threshold = _round_f32(iou_threshold)
     _need_cuda(boxes, scores, counts, category)
     b = _f32c(boxes)
     S, stride = b.shape[0], b.shape[1]

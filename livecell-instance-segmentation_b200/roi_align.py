@@ -146,27 +146,42 @@ class MultiScaleRoIAlign(nn.Module):
 
 def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
     """torchvision.ops.nms drop-in (TV:ops/boxes.py:20-48): int64 indices of the kept boxes, sorted by
-    decreasing score.  One host sync (the dense return type needs the count)."""
+    decreasing score.  One host sync (the dense return type needs the count).
+
+    The threshold is rounded to fp32 first, as torchvision's CUDA op does (the op the reference runs on a GPU);
+    nms_cpu_rule() keeps the CPU op's double comparison (see ops.nms_batched)."""
+    return _nms(boxes, scores, iou_threshold, False)
+
+
+def nms_cpu_rule(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    """nms() with torchvision's CPU-op threshold rule (fp32 IoU compared with the double threshold): differs from nms()
+    only for a pair whose IoU equals float32(iou_threshold) exactly.  The CPU-generated golden vectors follow this rule."""
+    return _nms(boxes, scores, iou_threshold, True)
+
+
+def _nms(boxes, scores, iou_threshold, cpu_threshold):
     if not boxes.is_cuda:
         raise _lib.LcrError("liblcr ops need CUDA tensors: the region pipeline has no CPU fallback")
+    thr = float(iou_threshold) if cpu_threshold else ops._round_f32(iou_threshold)
     ext = _ext.load()
     if ext is not None:
-        return ext.nms(boxes, scores, float(iou_threshold))
+        return ext.nms(boxes, scores, thr)
     n = boxes.shape[0]
     if n == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)
-    keep, kc = ops.nms_batched(boxes.reshape(1, n, 4), scores.reshape(1, n), float(iou_threshold), post_n=n)
+    keep, kc = ops.nms_batched(boxes.reshape(1, n, 4), scores.reshape(1, n), thr, post_n=n, cpu_threshold=True)
     return keep[0, : int(kc.item())].clone()
 
 
-def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float,
+                cpu_threshold: bool = False) -> torch.Tensor:
     """torchvision.ops.batched_nms drop-in (TV:ops/boxes.py:51-120), per-category semantics (boxes of
     different categories never interact), evaluated exactly — no coordinate-offset rounding."""
     n = boxes.shape[0]
     if n == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)
     keep, kc = ops.nms_batched(boxes.reshape(1, n, 4), scores.reshape(1, n), float(iou_threshold), post_n=n,
-                               category=idxs.reshape(1, n))
+                               category=idxs.reshape(1, n), cpu_threshold=cpu_threshold)
     return keep[0, : int(kc.item())].clone()
 
 

@@ -34,6 +34,16 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* Launchers such as torchrun export OMP_NUM_THREADS=1 to every rank; the CPU baseline leg of bench.py asks for the
+ * host's cores explicitly instead of inheriting that. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ---------------------------------------------------------------------------------------------
  * Anchors — src/components/anchor_generator.py:13-37.
  * base[a] (already rounded to fp32 by the caller, as torch.tensor(..., float32) does at :27) is

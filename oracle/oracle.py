@@ -43,6 +43,22 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def usable_cores() -> int:
+    """Cores this process may run on (cgroup/affinity aware), not what OMP_NUM_THREADS says."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
+def set_num_threads(n: int = 0) -> int:
+    """Use n OpenMP threads (0 = every usable core) regardless of an inherited OMP_NUM_THREADS (torchrun exports
+    OMP_NUM_THREADS=1 to its ranks, which made the r01 multi-GPU reference arm single-threaded).  Returns the count."""
+    n = int(n) if n and n > 0 else usable_cores()
+    lib().orc_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

@@ -1,0 +1,55 @@
+"""CPU side of the drop-in tests: the staged reference (baseline/_ref) imports and runs UNCHANGED through the drivers of
+tests/dropin_cases.py (untouched vs untouched — the harness, the stubs for matplotlib/gradio/pycocotools and the
+determinism assumptions are what is checked here; the untouched-vs-patched comparison needs the B200:
+tests/test_gpu_dropin.py).  Skipped where baseline/_ref was not staged."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import dropin_cases as dc  # noqa: E402
+import ref_harness  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_harness.available(), reason="baseline/_ref not staged (tools/stage_reference.py)")
+
+
+def test_manifest_matches_the_staged_files():
+    import hashlib
+    import json
+    with open(os.path.join(ref_harness.REF, "MANIFEST.json")) as f:
+        man = json.load(f)["files"]
+    assert "src/custom_maskrcnn.py" in man and len(man) >= 18
+    for rel, sha in man.items():
+        with open(os.path.join(ref_harness.REF, rel), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == sha, rel + " was modified after staging"
+
+
+def test_inference_driver_is_deterministic_on_cpu():
+    a, ia = dc.run_inference("cpu", False, 96, 128, 2, seed=0, n_cells=20)
+    b, ib = dc.run_inference("cpu", False, 96, 128, 2, seed=0, n_cells=20, state=ia["state"])
+    assert ia["roi_align_type"].startswith("torchvision")
+    assert dc.compare_predictions(a, b, score_atol=0.0) == 0
+    assert sum(len(p["boxes"]) for p in a) > 0, "the randomly initialised model should produce detections"
+
+
+def test_train_step_driver_has_positives_and_repeats_on_cpu():
+    la, ga, _ = dc.run_train_step("cpu", False, B=2, H=128, W=128)
+    lb, gb, _ = dc.run_train_step("cpu", False, B=2, H=128, W=128)
+    assert set(la) == {"loss_rpn_cls", "loss_box_cls", "loss_box_reg", "loss_mask"}
+    assert la["loss_mask"] > 0 and la["loss_box_reg"] > 0, "synthetic GT must give foreground proposals (all loss branches)"
+    for k in la:
+        assert abs(la[k] - lb[k]) <= 1e-6 * max(1.0, abs(la[k]))
+    assert any(n.startswith("fpn.") for n in ga) and any(n.startswith("layer1.") for n in ga)
+    assert max(dc.rel_err(ga[n], gb[n]) for n in ga) < 1e-5
+
+
+def test_scripts_import_unchanged_with_stubs(tmp_path):
+    metrics, val, info = dc.run_train_epoch("cpu", False, n_batches=1, B=2, H=128, W=128)
+    assert np.isfinite(metrics["total_loss"]) and metrics["gradient_norm_mean"] > 0
+    assert "mean_iou" in val and info["roi_align_type"].startswith("torchvision")
+    status, shape, _ = dc.run_gradio_predict("cpu", False, tmp_path, H=96, W=128)
+    assert status.startswith("Detected ") and len(shape) == 3
+    preds, summary, _ = dc.run_tiles("cpu", False, tmp_path, n_tiles=1)
+    assert preds[0]["masks"].dtype == np.uint8 and preds[0]["masks"].shape[1:] == (222, 300)

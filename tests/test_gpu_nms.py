@@ -13,10 +13,12 @@ def ops():
     return o
 
 
-def gpu_nms(boxes, scores, thr):
+def gpu_nms(boxes, scores, thr, cpu_threshold=True):
+    """cpu_threshold=True: the CPU op's rule (fp32 IoU vs the double threshold) — what the CPU-generated golden vectors
+    and the oracle follow; False = the drop-in's default, torchvision's CUDA rule (threshold rounded to fp32)."""
     from gpu_util import N, T
-    from livecell_instance_segmentation_b200.roi_align import nms
-    out = nms(T(boxes), T(scores), thr)
+    from livecell_instance_segmentation_b200.roi_align import nms, nms_cpu_rule
+    out = (nms_cpu_rule if cpu_threshold else nms)(T(boxes), T(scores), thr)
     assert out.dtype == torch.int64
     return N(out)
 
@@ -36,6 +38,24 @@ def test_known_answer_probes(golden):
     assert np.array_equal(gpu_nms(g["zero_boxes"], g["zero_scores"], 0.4), g["zero_keep"])  # NaN IoU never suppresses
     assert np.array_equal(gpu_nms(g["nan_boxes"], g["nan_scores"], 0.4), g["nan_keep"])     # NaN score first
     assert gpu_nms(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), 0.5).shape == (0,)
+
+
+def test_threshold_rule_matches_torchvision_cuda(golden):
+    """for a pair whose fp32 IoU equals float32(thr) exactly, torchvision's CPU op suppresses
+    (0.4f > 0.4 as doubles) and its CUDA op, which the reference runs on a GPU, does not (threshold rounded to fp32).
+    The drop-in's default must follow the CUDA op on this device; cpu_threshold=True keeps the CPU rule."""
+    import torchvision
+    from gpu_util import N, T
+    g = golden("nms")
+    for name in ("eq", "tie", "zero", "nan"):
+        b, s = g[f"{name}_boxes"], g[f"{name}_scores"]
+        for thr in (0.4, 0.5):
+            tv = N(torchvision.ops.nms(T(b), T(s), thr))
+            assert np.array_equal(gpu_nms(b, s, thr, cpu_threshold=False), tv), (name, thr)
+    # the two rules really differ on the exact-tie probe (otherwise this test pins nothing)
+    cpu_rule = gpu_nms(g["eq_boxes"], g["eq_scores"], 0.4, cpu_threshold=True)
+    cuda_rule = gpu_nms(g["eq_boxes"], g["eq_scores"], 0.4, cpu_threshold=False)
+    assert np.array_equal(cpu_rule, g["eq_keep_04"]) and not np.array_equal(cpu_rule, cuda_rule)
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 257, 1000, 2047, 2048, 2049, 5000])

@@ -60,8 +60,14 @@ def synth_targets(B, H, W, seed, device):
 
 
 def _deterministic():
+    """Deterministic cuDNN algorithms and NO TF32: with TF32 (torch's cuDNN default) a 1e-7 difference in a pooled feature
+    is re-rounded to a 10-bit mantissa inside every convolution of the heads and comes out as 1e-3 — the untouched model
+    then differs from ITSELF by 1e-3 between two runs (atomics in torchvision's RoIAlign backward), which would hide what
+    these tests measure: the difference our kernels introduce."""
     torch.backends.cudnn.benchmark = False
     torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def new_model(cm, device, seed=0, channels_last=False, state=None):
@@ -76,6 +82,23 @@ def new_model(cm, device, seed=0, channels_last=False, state=None):
     return model
 
 
+def calibrate_rpn(model, images, target_std=0.3):
+    """A randomly initialised RPN scores every anchor 0.5 +- 0.002, so the top-k post-sigmoid values collide in fp32
+    and torch.topk's (unspecified) tie order decides the proposals.  Scale the objectness layer so that the level-0
+    logits have std `target_std` on `images` (in the model's current train/eval mode): scores spread over ~0.3-0.8 like
+    a briefly trained model and the top-k is tie-free.  Pure function of (weights, images): the untouched and the
+    patched run calibrate identically.  BatchNorm buffers are restored afterwards."""
+    saved = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        feats, _ = model.extract_features(images)
+        cls, _ = model.rpn(feats)
+        gain = float(target_std / cls[0].std().clamp(min=1e-12))
+    model.load_state_dict(saved)
+    with torch.no_grad():
+        model.rpn.cls_logits.weight.mul_(gain)
+    return gain
+
+
 def _install(patched):
     if patched:
         from livecell_instance_segmentation_b200 import install as inst
@@ -85,13 +108,21 @@ def _install(patched):
     return None
 
 
-def rpn_scores_tie_free(model, images, k=251):
+def rpn_scores_tie_free(model, images, k=251, only_first=False):
     """The top-(k) post-sigmoid level-0 scores of every image are distinct (torch.topk's tie order is unspecified, so
-    top-k index parity is only defined on tie-free inputs — SURVEY §8a2)."""
+    top-k index parity is only defined on tie-free inputs — SURVEY §8a2).  Restores BatchNorm buffers (train mode)."""
+    saved = {k_: v.detach().clone() for k_, v in model.state_dict().items()}
+    try:
+        return _tie_free(model, images, k, only_first)
+    finally:
+        model.load_state_dict(saved)
+
+
+def _tie_free(model, images, k, only_first):
     with torch.no_grad():
         feats, _ = model.extract_features(images)
         cls, _ = model.rpn(feats)
-        for b in range(cls[0].shape[0]):
+        for b in range(1 if only_first else cls[0].shape[0]):
             s = torch.sigmoid(cls[0][b]).reshape(-1)
             top = torch.topk(s, min(k, s.numel())).values
             if torch.unique(top).numel() != top.numel():
@@ -109,6 +140,8 @@ def run_inference(device, patched, H, W, B, seed=0, channels_last=False, n_cells
         images = torch.from_numpy(np.stack([synth_image(H, W, n_cells, 100 * seed + b) for b in range(B)])).to(device)
         if channels_last:
             images = images.contiguous(memory_format=torch.channels_last)
+        if state is None:
+            calibrate_rpn(model, images)
         with torch.no_grad():
             preds = model(images)
         out = [{k: v.detach().cpu().numpy() for k, v in p.items()} for p in preds]
@@ -130,6 +163,14 @@ def run_train_step(device, patched, B=8, H=256, W=256, seed=0, state=None, chann
         model = new_model(cm, device, seed, channels_last, state).train()
         images = torch.from_numpy(np.stack([synth_image(H, W, 40, 7 + b) for b in range(B)])).to(device)
         targets = synth_targets(B, H, W, 5, device)
+        base_w = model.rpn.cls_logits.weight.detach().clone()
+        for std in (0.3, 0.45, 0.6, 0.2, 0.9):                 # first calibration whose top-501 of image 0 is tie-free
+            with torch.no_grad():
+                model.rpn.cls_logits.weight.copy_(base_w)
+            calibrate_rpn(model, images, std)
+            tie_free = rpn_scores_tie_free(model, images, k=501, only_first=True)   # forward_train selects from image 0 only
+            if tie_free:
+                break
         torch.manual_seed(1234)                     # the randperm draws of rpn.compute_loss / sample_proposals
         loss_dict = model(images, targets)
         total = sum(v for v in loss_dict.values())
@@ -137,7 +178,7 @@ def run_train_step(device, patched, B=8, H=256, W=256, seed=0, state=None, chann
         total.backward()
         losses = {k: float(v.detach().cpu()) for k, v in loss_dict.items()}
         grads = {n: p.grad.detach().cpu().numpy().copy() for n, p in model.named_parameters() if p.grad is not None}
-        return losses, grads, {"roi_align_type": type(model.roi_align).__module__}
+        return losses, grads, {"roi_align_type": type(model.roi_align).__module__, "tie_free": tie_free}
     finally:
         if inst is not None:
             inst.uninstall()
@@ -174,6 +215,8 @@ def run_train_epoch(device, patched, n_batches=2, B=4, H=256, W=256):
             imgs = tuple(torch.from_numpy(synth_image(H, W, 40, 50 + 10 * i + b)) for b in range(B))
             tg = tuple({k: v.cpu() for k, v in t.items()} for t in synth_targets(B, H, W, 90 + i, "cpu"))
             batches.append((imgs, tg))
+        model.train()
+        calibrate_rpn(model, torch.stack([i.to(device) for i in batches[0][0]]))
         torch.manual_seed(4321)
         metrics = tc.train_one_epoch(model, _Loader(batches), opt, device, epoch=1)
         val = tc.evaluate(model, _Loader(batches[:1]), device)
@@ -195,8 +238,12 @@ def run_gradio_predict(device, patched, tmpdir, H=520, W=704):
     try:
         torch.manual_seed(0)
         ckpt = os.path.join(str(tmpdir), "custom_model.pth")
-        if not os.path.exists(ckpt):
-            torch.save({"model_state_dict": cm.get_custom_model(num_classes=2).state_dict()}, ckpt)
+        frame = (synth_image(H, W, 150, 3)[0] * 255).astype(np.uint8)
+        frame = np.repeat(frame[:, :, None], 3, axis=2)
+        if not os.path.exists(ckpt):          # written by the untouched run, read back by the patched one
+            m0 = cm.get_custom_model(num_classes=2).eval()
+            calibrate_rpn(m0, torch.from_numpy(frame).permute(2, 0, 1).float().div(255)[None])
+            torch.save({"model_state_dict": m0.state_dict()}, ckpt)
         app = importlib.import_module("app_gradio")
         app.DEVICE = torch.device(device)
         captured = {}
@@ -208,8 +255,6 @@ def run_gradio_predict(device, patched, tmpdir, H=520, W=704):
             return captured["model"]
 
         app.load_model = load_and_keep
-        frame = (synth_image(H, W, 150, 3)[0] * 255).astype(np.uint8)
-        frame = np.repeat(frame[:, :, None], 3, axis=2)
         result_img, status = app.predict_single_image(frame, ckpt, 0.5)
         return status, np.asarray(result_img).shape, {"roi_align_type": type(captured["model"].roi_align).__module__}
     finally:
@@ -237,6 +282,8 @@ def run_tiles(device, patched, tmpdir, n_tiles=3):
                 Image.fromarray(arr).save(path)
             tiles.append({"path": path, "tile_num": t, "filename": os.path.basename(path)})
         model = new_model(cm, device, 0).eval()
+        first = transforms.ToTensor()(Image.open(tiles[0]["path"]).convert("RGB")).to(device)[None]
+        calibrate_rpn(model, first)
         results = vis.predict_on_tiles(model, tiles, torch.device(device), transforms.Compose([transforms.ToTensor()]))
         kept = vis.filter_detections_by_border_mini_tiles(results, score_threshold=0.5, mask_threshold=0.4)
         preds = [{k: v.numpy() for k, v in r["prediction"].items()} for r in results]

@@ -1128,6 +1128,368 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
   }
 }
 
+// ---- forward, staged rows (P = 7, dense NHWC, C in {64, 128, 192, 256}) ------------------------------
+// The north-star design: the feature window of a RoI is STAGED through shared memory by the copy engine.
+//
+// Why: roi_fwd_warp_kernel keeps the gather in the pooling warps — per window row a warp issues 21-28 loads, waits
+// one L2 round trip (~600 cycles under load), does its FMAs, and starts over: ~15 such round trips per item plus the
+// table build and the tile store, all on ONE warp's critical path, 16 warps per SM.  The L2 -> SM path itself is
+// nowhere near its limit (tools/l2_probe.cu: 15-19 TB/s from L2 with >= 64 KB in flight per SM, the gather of a bench
+// step is 11 GB), the chain is.  Here the chain is cut:
+//
+//   * In dense NHWC memory the 256 channels of `ncols` neighbouring pixels of a map row are ONE contiguous run of
+//     ncols KB, so a window row is a single 1-D bulk copy (cp.async.bulk.shared.global, SASS UBLKCP — the TMA engine
+//     without a tensor map; a tensor map's box is fixed per map, window widths vary per RoI).
+//   * One PRODUCER warp per CTA builds the tables of the CTA's RoIs one to two RoIs ahead and issues the row copies
+//     into a 56 KB byte ring (rows are 4-28 KB; allocation wraps at row boundaries), each row on its own mbarrier:
+//     ~45 KB in flight per CTA, two CTAs per SM.
+//   * Four CONSUMER warps (warp = 64-channel group, lane = channel pair) wait for a row, pool it in x with the same
+//     bin-dense folded weights as the warp kernel — LDS.64 at ~30 cycles instead of LDG at ~600 — release it, and
+//     accumulate in y with the two-row cache.  Output tile and bulk store as before (one 12.5 KB store per warp).
+//   * RoIs whose bins are wider than 4 feature pixels (samples more than 2 px apart: a contiguous span would be mostly
+//     unused columns) or whose span exceeds 28 columns are gathered from global memory by the consumers, as before.
+//
+// Arithmetic is exactly that of roi_warp_body (same folded weights, same FMA order): results are bit-identical to
+// roi_fwd_warp_kernel.
+constexpr int kStRing = 56 * 1024;  // default byte ring of staged rows (two CTAs per SM)
+constexpr int kStBars = 16;         // rows in flight (mbarrier slots)
+constexpr int kStDescs = 4;         // RoI descriptors (tables) built ahead
+constexpr int kStMaxCols = 28;      // widest staged row in pixels (28 KB at C = 256: two fit in the ring)
+
+struct __align__(16) StagedDesc {
+  WarpTables<7> tb;
+  int run;             // widest bin run in columns; -1: dead RoI (zero tile)
+  int staged;          // 1: rows arrive through the ring, 0: consumers gather from global memory
+  int b, lvl;
+  uint32_t col0_bytes;  // byte offset of the first staged column inside a map row
+  uint32_t row_bytes;   // staged bytes per row
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// One staged window row -> T[0..XB) = this lane's x-bins (x-pooled), then the row's ring space is handed back to the
+// producer.
+template <int XB, int NB, int CSW>
+__device__ __forceinline__ void pool_row_staged(const unsigned char* __restrict__ ring_lane, const uint32_t (&xo)[XB],
+                                                const float (&xw)[XB][NB], const uint32_t* __restrict__ row_off, uint64_t* full,
+                                                uint64_t* empty, uint32_t& q, uint32_t csb, float2 (&T)[XB]) {
+  const uint32_t cs = CSW ? (uint32_t)CSW * 4u : csb;
+  const uint32_t i = q % kStBars;
+  mbar_wait(&full[i], (q / kStBars) & 1u);
+  const unsigned char* row = ring_lane + row_off[i];
+  float2 v[XB][NB];
+#pragma unroll
+  for (int pw = 0; pw < XB; ++pw) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) v[pw][j] = *reinterpret_cast<const float2*>(row + xo[pw] + j * cs);
+  }
+#pragma unroll
+  for (int pw = 0; pw < XB; ++pw) {
+    float2 t = __fmul2_rn(splat(xw[pw][0]), v[pw][0]);
+#pragma unroll
+    for (int j = 1; j < NB; ++j) t = ffma2(splat(xw[pw][j]), v[pw][j], t);
+    T[pw] = t;
+  }
+  __syncwarp();  // every lane's loads of this row have returned (their FMAs consumed them)
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[i]);
+  ++q;
+}
+
+// roi_warp_body with the rows coming from the ring (P = 7; XB = 7: one bin group per warp, XB = 4: two).
+template <int XB, int NB, int CSW>
+__device__ __forceinline__ void roi_warp_body_staged(const WarpTables<7>& tb, int xb0, const unsigned char* __restrict__ ring_lane,
+                                                     uint32_t col0_bytes, uint32_t csb, const uint32_t* __restrict__ row_off,
+                                                     uint64_t* full, uint64_t* empty, uint32_t& q, float* __restrict__ my,
+                                                     bool& tile_free) {
+  constexpr int P = 7, PP = 49;
+  constexpr uint32_t kAll = 0xffffffffu;
+  float2 T0[XB], T1[XB], acc[XB];
+  uint32_t xo[XB];
+  float xw[XB][NB];
+#pragma unroll
+  for (int pw = 0; pw < XB; ++pw) {
+    T0[pw] = T1[pw] = acc[pw] = make_float2(0.f, 0.f);
+    xo[pw] = tb.xoff[xb0 + pw] - col0_bytes;
+    const float4 w = tb.xw[xb0 + pw];
+    xw[pw][0] = w.x;
+    xw[pw][1] = w.y;
+    xw[pw][2] = w.z;
+    if (NB > 3) xw[pw][3 % NB] = w.w;
+  }
+  const bool lower = XB != 7 || (threadIdx.x & 16) == 0;  // XB = 7: conflict-free tile stores, see roi_warp_body
+  float* const o_a = my + (lower ? 0 : PP);
+  float* const o_b = my + (lower ? PP : 0);
+  const int nmine = min(XB, P - xb0);
+  bool flip = false;
+#pragma unroll 1
+  for (int t = 0; t < 2 * P; ++t) {
+    const uint32_t m = tb.ymode[t];
+    if (__any_sync(kAll, m & kValid)) {
+      const uint32_t mode = m & kModeMask;
+      const AxisTapB s = tb.ys[t];
+      const float2 wl = splat(s.w_lo * 0.25f), wh = splat(s.w_hi * 0.25f);
+      const bool border = __any_sync(kAll, m & kBorder);
+      const bool is_new = __any_sync(kAll, mode == kNew), is_shift = __any_sync(kAll, mode == kShift);
+      auto y_step = [&](auto& LO, auto& HI) -> bool {
+        if (is_new || (is_shift && !border)) pool_row_staged<XB, NB, CSW>(ring_lane, xo, xw, row_off, full, empty, q, csb, LO);
+        if (is_shift && !border) {
+#pragma unroll
+          for (int pw = 0; pw < XB; ++pw) {
+            acc[pw] = ffma2(wl, HI[pw], acc[pw]);
+            acc[pw] = ffma2(wh, LO[pw], acc[pw]);
+          }
+          return true;
+        }
+        if (is_shift) {
+#pragma unroll
+          for (int pw = 0; pw < XB; ++pw) LO[pw] = HI[pw];
+        } else if (is_new) {
+          if (border) {
+#pragma unroll
+            for (int pw = 0; pw < XB; ++pw) HI[pw] = LO[pw];
+          } else {
+            pool_row_staged<XB, NB, CSW>(ring_lane, xo, xw, row_off, full, empty, q, csb, HI);
+          }
+        }
+#pragma unroll
+        for (int pw = 0; pw < XB; ++pw) {
+          acc[pw] = ffma2(wl, LO[pw], acc[pw]);
+          acc[pw] = ffma2(wh, HI[pw], acc[pw]);
+        }
+        return false;
+      };
+      if (!flip) flip = y_step(T0, T1);
+      else flip = !y_step(T1, T0);
+    }
+    if (t & 1) {  // bin row complete
+      if (!tile_free) {  // the previous RoI's bulk store must have finished READING the tile (first write only)
+        if ((threadIdx.x & 31) == 0) bulk_wait_read_all();
+        __syncwarp();
+        tile_free = true;
+      }
+      const int o = (t >> 1) * P;
+#pragma unroll
+      for (int pw = 0; pw < XB; ++pw) {
+        const float e = acc[pw].x, f = acc[pw].y;
+        if (pw < nmine) {
+          o_a[o + pw] = lower ? e : f;
+          o_b[o + pw] = lower ? f : e;
+        }
+        acc[pw] = make_float2(0.f, 0.f);
+      }
+    }
+  }
+}
+
+// XB = 7: 4 consumer warps of 64 channels; XB = 4: 8 consumer warps of 32 channels (half-warps take bins 0-3 / 4-6).  The
+// output tile belongs to the RoI (C x 49 floats), not to a warp, so more pooling warps cost no shared memory — the
+// warp kernel cannot do that (one 12.5 KB tile per warp caps it at 16 warps per SM).
+template <int XB, int CSW>
+__global__ void __launch_bounds__((256 / WarpItem<7, XB>::kChannels + 2) * 32, 2)
+    roi_fwd_staged_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out, int rois_per_cta, int flags,
+                          uint32_t ring_bytes) {
+  using WI = WarpItem<7, XB>;
+  constexpr int WARPS = 256 / WI::kChannels;  // consumer warps at C = 256
+  constexpr int PP = 49;
+  constexpr uint32_t kAll = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* ring = smem_raw;
+  float* tile_roi = reinterpret_cast<float*>(smem_raw + ring_bytes);  // [C][49] of the RoI being pooled
+  StagedDesc* descs = reinterpret_cast<StagedDesc*>(smem_raw + ring_bytes + sizeof(float) * 256 * PP);
+  uint64_t* full = reinterpret_cast<uint64_t*>(descs + kStDescs);
+  uint64_t* empty = full + kStBars;
+  uint64_t* dfull = empty + kStBars;
+  uint64_t* dempty = dfull + kStDescs;
+  uint32_t* row_off = reinterpret_cast<uint32_t*>(dempty + kStDescs);
+  const int warp = __shfl_sync(kAll, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int ncw = p.C / WI::kChannels;  // active consumer warps (C is a multiple of 64, at most 256)
+  const uint32_t csb = (uint32_t)p.C * 4u;
+  const int k_begin = blockIdx.x * rois_per_cta;
+  const int k_end = min(p.K, k_begin + rois_per_cta);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStBars; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], (uint32_t)ncw);
+    }
+    for (int i = 0; i < kStDescs; ++i) {
+      mbar_init(&dfull[i], 1);
+      mbar_init(&dempty[i], (uint32_t)ncw + 1u);  // the pooling warps and the row issuer
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == WARPS) {
+    // ---------------- table builder: geometry, taps and folded weights of the CTA's RoIs, kStDescs - 1 RoIs ahead ----------
+    for (int k = k_begin; k < k_end; ++k) {
+      const int r = k - k_begin, d = r % kStDescs;
+      if (r >= kStDescs) mbar_wait(&dempty[d], (uint32_t)((r / kStDescs) - 1) & 1u);  // consumers and issuer are done with the slot
+      StagedDesc& ds = descs[d];
+      const RoiGeom g = roi_geom(p, k);
+      const bool live = __any_sync(kAll, g.live);
+      const int lvl = live ? g.lvl : 0;
+      const LvParam& lv = p.lv[lvl];
+      int run = -1, staged = 0;
+      uint32_t col0b = 0, rowb = 0;
+      if (live) {
+        run = build_tables_warp<7>(ds.tb, g, lv, lane, WI::kHalves * XB);
+        if (run <= 4) {
+          const int nb = run <= 3 ? 3 : 4;
+          int f = lane < 7 ? ds.tb.xfirst[lane] : 0x7fffffff;
+          int l = lane < 7 ? ds.tb.xfirst[lane] + nb - 1 : -1;
+          f = __reduce_min_sync(kAll, f);
+          l = __reduce_max_sync(kAll, l);
+          const int ncols = l - f + 1;
+          if (ncols <= kStMaxCols && (uint32_t)ncols * csb * 2u <= ring_bytes && !(flags & 4)) {
+            staged = 1;
+            col0b = (uint32_t)f * csb;
+            rowb = (uint32_t)ncols * csb;
+          }
+        }
+      }
+      if (lane == 0) {
+        ds.run = run;
+        ds.staged = staged;
+        ds.b = g.b;
+        ds.lvl = lvl;
+        ds.col0_bytes = col0b;
+        ds.row_bytes = rowb;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dfull[d]);  // release: tables and header are visible to whoever observes the phase
+    }
+  } else if (warp == WARPS + 1) {
+    // ---------------- row issuer (one thread): the RoIs' window rows into the ring, in consumption order ----------------
+    if (lane == 0) {
+      uint32_t q = 0, tail_q = 0, head = 0, tail_off = 0;
+      int inflight = 0;
+      bool wrapped = false;
+      for (int k = k_begin; k < k_end; ++k) {
+        const int r = k - k_begin, d = r % kStDescs;
+        mbar_wait(&dfull[d], (uint32_t)(r / kStDescs) & 1u);
+        const StagedDesc& ds = descs[d];
+        if (ds.staged) {
+          const LvParam& lv = p.lv[ds.lvl];
+          const uint32_t rowb = ds.row_bytes;
+          const char* fbase = reinterpret_cast<const char*>(lv.data + (size_t)ds.b * lv.sn) + ds.col0_bytes;
+          auto issue = [&](uint32_t row_byte_off) {
+            uint32_t place = 0;
+            for (;;) {
+              bool ok = false, wrap_now = false;
+              if (inflight == 0) {
+                head = 0;
+                wrapped = false;
+                place = 0;
+                ok = true;
+              } else if (!wrapped) {
+                if (head + rowb <= ring_bytes) {
+                  place = head;
+                  ok = true;
+                } else if (rowb <= tail_off) {
+                  place = 0;
+                  wrap_now = true;
+                  ok = true;
+                }
+              } else if (head + rowb <= tail_off) {
+                place = head;
+                ok = true;
+              }
+              if (ok && inflight < kStBars) {
+                if (wrap_now) wrapped = true;
+                break;
+              }
+              // hand the oldest row's space back (rows are released in issue order)
+              mbar_wait(&empty[tail_q % kStBars], (tail_q / kStBars) & 1u);
+              ++tail_q;
+              --inflight;
+              if (inflight > 0) {
+                const uint32_t nt = row_off[tail_q % kStBars];
+                if (nt < tail_off) wrapped = false;  // the tail itself wrapped to the front
+                tail_off = nt;
+              }
+            }
+            const uint32_t i = q % kStBars;
+            row_off[i] = place;
+            if (inflight == 0) tail_off = place;
+            mbar_expect_tx(&full[i], rowb);
+            bulk_load_global_to_smem(ring + place, fbase + row_byte_off, rowb, &full[i]);
+            head = place + rowb;
+            ++q;
+            ++inflight;
+          };
+#pragma unroll 1
+          for (int t = 0; t < 14; ++t) {
+            const uint32_t m = ds.tb.ymode[t];
+            if (!(m & kValid)) continue;
+            const uint32_t mode = m & kModeMask;
+            const bool border = (m & kBorder) != 0;
+            const AxisTapB s = ds.tb.ys[t];
+            if (mode == kNew) {
+              issue(s.off_lo);
+              if (!border) issue(s.off_hi);
+            } else if (mode == kShift && !border) {
+              issue(s.off_hi);
+            }
+          }
+        }
+        mbar_arrive(&dempty[d]);
+      }
+    }
+  } else if (warp < ncw) {
+    // ---------------- consumers: warp = channel group of every RoI of the CTA ----------------
+    const int pair = lane % WI::kPairs;
+    const int xb0 = (lane / WI::kPairs) * XB;
+    const int c0 = warp * WI::kChannels;
+    float* tile = tile_roi + (size_t)c0 * PP;                     // this warp's slice of the RoI tile
+    float* my = tile + (size_t)(2 * pair) * PP + xb0;
+    const unsigned char* ring_lane = ring + (size_t)(c0 + 2 * pair) * 4;
+    const uint64_t pol = l2_policy_evict_first();
+    uint32_t q = 0;
+    bool tile_free = true;
+    for (int k = k_begin; k < k_end; ++k) {
+      const int r = k - k_begin, d = r % kStDescs;
+      mbar_wait(&dfull[d], (uint32_t)(r / kStDescs) & 1u);
+      const StagedDesc& ds = descs[d];
+      const int run = ds.run;
+      if (run >= 0 && ds.staged) {
+        if (run <= 3) roi_warp_body_staged<XB, 3, CSW>(ds.tb, xb0, ring_lane, ds.col0_bytes, csb, row_off, full, empty, q, my, tile_free);
+        else roi_warp_body_staged<XB, 4, CSW>(ds.tb, xb0, ring_lane, ds.col0_bytes, csb, row_off, full, empty, q, my, tile_free);
+      } else {
+        if (!tile_free) {
+          if (lane == 0) bulk_wait_read_all();
+          __syncwarp();
+          tile_free = true;
+        }
+        if (run < 0) {
+          for (int j = lane; j < WI::kTileFloats; j += 32) tile[j] = 0.f;
+        } else {
+          const LvParam& lv = p.lv[ds.lvl];
+          const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)ds.b * lv.sn + c0 + 2 * pair);
+          const uint32_t swb = (uint32_t)lv.sw * 4u;
+          if (run <= 3) roi_warp_body<7, XB, 3, CSW>(ds.tb, xb0, fb, swb, my);
+          else if (run == 4) roi_warp_body<7, XB, 4, CSW>(ds.tb, xb0, fb, swb, my);
+          else roi_warp_body<7, XB, 0, CSW>(ds.tb, xb0, fb, swb, my);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();  // the warp's slice is complete and every lane is done with the descriptor
+      if (lane == 0) {
+        float* dst = out + ((size_t)k * p.C + c0) * PP;
+        const uint32_t bytes = (uint32_t)(WI::kChannels * PP * sizeof(float));
+        if (flags & 1) bulk_store_smem_to_global_hint(dst, tile, bytes, pol);
+        else bulk_store_smem_to_global(dst, tile, bytes);
+        bulk_commit();
+        mbar_arrive(&dempty[d]);
+      }
+      tile_free = false;
+    }
+    if (lane == 0) bulk_wait_read_all();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1275,6 +1637,48 @@ static bool all_sw_equal(const RoiParams& p, long long v) {
   return true;
 }
 
+
+// staged forward: P = 7, every level dense NHWC (sc == 1, sw == C), C a multiple of 64 up to 256, 16-byte aligned maps
+static bool staged_eligible(const RoiParams& p) {
+  if (p.PH != 7 || p.C % 64 != 0 || p.C > 256) return false;
+  for (int l = 0; l < p.L; ++l) {
+    const LvParam& v = p.lv[l];
+    if (v.sc != 1 || v.sw != p.C || v.sh != (long long)v.W * p.C || v.sn % 4 != 0 || !aligned_to(v.data, 16)) return false;
+    if (v.W < 4) return false;
+  }
+  return true;
+}
+
+template <int XB, int CSW>
+static int launch_fwd_staged(const RoiParams& p, float* out, cudaStream_t st, int flags) {
+  using WI = WarpItem<7, XB>;
+  constexpr int WARPS = 256 / WI::kChannels;
+  size_t ring = kStRing;
+  if (const char* v = getenv("LCR_ROI_RING_KB")) ring = (size_t)(atoi(v) > 0 ? atoi(v) : 56) * 1024;  // > 56: one CTA per SM
+  const size_t fixed = sizeof(float) * 256 * 49 + kStDescs * sizeof(StagedDesc) + (2 * kStBars + 2 * kStDescs) * sizeof(uint64_t) +
+                       kStBars * sizeof(uint32_t);
+  if (ring + fixed > 227 * 1024) ring = (227 * 1024 - fixed) / 1024 * 1024;
+  const size_t smem = ring + fixed;
+  // RoIs per CTA: long enough to amortise the pipeline fill, short enough that small K still covers every SM twice
+  int rpc = p.K / (2 * sm_count());
+  rpc = rpc < 1 ? 1 : (rpc > 8 ? 8 : rpc);
+  if (const char* v = getenv("LCR_ROI_RPC")) rpc = atoi(v) > 0 ? atoi(v) : rpc;
+  const long long want = ((long long)p.K + rpc - 1) / rpc;
+  LCR_REQUIRE(want < (1ll << 31), LCR_ERR_CAPACITY);
+  auto kern = roi_fwd_staged_kernel<XB, CSW>;
+  static thread_local int configured_dev = -1;
+  static thread_local size_t configured_smem = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev || configured_smem != smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    configured_dev = dev;
+    configured_smem = smem;
+  }
+  kern<<<(unsigned)want, (WARPS + 2) * 32, smem, st>>>(p, out, rpc, flags, (uint32_t)ring);
+  return after_launch();
+}
 }  // namespace lcr
 
 using namespace lcr;
@@ -1288,6 +1692,16 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
   LCR_REQUIRE(out, LCR_ERR_INVALID_ARG);
   cudaStream_t st = as_stream(stream);
   if (fast_eligible(p, out)) {
+    // roi_fwd_staged_kernel (the north star's "window staged through TMA into shared memory") is complete, bit-identical and
+    // covered by the GPU tests, but measured SLOWER than the warp kernel on B200 (bench list 1.60 vs 1.46 ms,
+    // profiles/r02_roi_staged_ab.jsonl): staging moves every window byte through the SM's 128 B/clk shared-memory data path
+    // twice (copy-engine fill + LDS) where a global load passes once.  It is therefore opt-in: LCR_ROI_FWD=staged.
+    if (PH == 7 && staged_eligible(p) && (env_is("LCR_ROI_FWD", "staged") || env_is("LCR_ROI_FWD", "staged_direct"))) {
+      // flags: bit 0 = evict-first output stores, bit 2 = stage nothing (every RoI gathered by the consumers: A/B)
+      const int flags = (env_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (env_is("LCR_ROI_FWD", "staged_direct") ? 4 : 0);
+      if (env_is("LCR_ROI_STAGED_WARPS", "4")) return p.C == 256 ? launch_fwd_staged<7, 256>(p, out, st, flags) : launch_fwd_staged<7, 0>(p, out, st, flags);
+      return p.C == 256 ? launch_fwd_staged<4, 256>(p, out, st, flags) : launch_fwd_staged<4, 0>(p, out, st, flags);
+    }
     if (warp_eligible(p) && !env_is("LCR_ROI_FWD", "cta")) {
       // (P = 7 with 32-channel items — half-warps taking x-bins 0-3 / 4-6, XB = 4, 6 CTAs/SM instead of 4 — was measured
       // 10 % slower than the 64-channel items on B200: the extra occupancy does not pay for the 8-slots-for-7-bins padding.)

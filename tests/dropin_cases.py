@@ -99,6 +99,24 @@ def calibrate_rpn(model, images, target_std=0.3):
     return gain
 
 
+def perturb_roi_align_by_one_ulp(model, seed=99):
+    """Yardstick for 'how far may a correct replacement be': the UNTOUCHED model with every pooled feature moved by one
+    to two fp32 ulps (x * (1 +- 2^-23), random sign; 1.2e-7 relative, a hundredth of the 1e-5 parity bound).  A different summation order inside RoIAlign does exactly this to
+    the forward result; whatever the rest of the network (BatchNorm in train mode, AdamW's g/|g| first step, a top-k
+    edge) amplifies it to is the reference's own sensitivity, not an error of the replacement."""
+    inner = model.roi_align.forward
+    gen = {}
+
+    def forward(x, rois):
+        out = inner(x, rois)
+        g = gen.setdefault(out.device, torch.Generator(device=out.device).manual_seed(seed))
+        sign = torch.randint(0, 2, out.shape, generator=g, device=out.device, dtype=torch.int8).to(out.dtype) * 2 - 1
+        return out * (1.0 + sign * 2.0 ** -23)
+
+    model.roi_align.forward = forward
+    return model
+
+
 def _install(patched):
     if patched:
         from livecell_instance_segmentation_b200 import install as inst
@@ -154,7 +172,7 @@ def run_inference(device, patched, H, W, B, seed=0, channels_last=False, n_cells
         ref_harness.purge()
 
 
-def run_train_step(device, patched, B=8, H=256, W=256, seed=0, state=None, channels_last=False):
+def run_train_step(device, patched, B=8, H=256, W=256, seed=0, state=None, channels_last=False, perturb=False):
     """forward_train + backward (custom_maskrcnn.py:85-142, train_custom.py:40-44) -> (losses, {param: grad})."""
     _deterministic()
     cm = ref_harness.import_reference()
@@ -171,6 +189,9 @@ def run_train_step(device, patched, B=8, H=256, W=256, seed=0, state=None, chann
             tie_free = rpn_scores_tie_free(model, images, k=501, only_first=True)   # forward_train selects from image 0 only
             if tie_free:
                 break
+        if perturb:
+            assert not patched
+            perturb_roi_align_by_one_ulp(model)
         torch.manual_seed(1234)                     # the randperm draws of rpn.compute_loss / sample_proposals
         loss_dict = model(images, targets)
         total = sum(v for v in loss_dict.values())
@@ -198,7 +219,7 @@ class _Loader:
         return len(self.batches)
 
 
-def run_train_epoch(device, patched, n_batches=2, B=4, H=256, W=256):
+def run_train_epoch(device, patched, n_batches=2, B=4, H=256, W=256, perturb=False):
     """train_custom.train_one_epoch + evaluate, imported UNCHANGED (stub matplotlib/wandb/pycocotools), driven with a
     synthetic loader (train_custom.py:21-166)."""
     _deterministic()
@@ -217,6 +238,9 @@ def run_train_epoch(device, patched, n_batches=2, B=4, H=256, W=256):
             batches.append((imgs, tg))
         model.train()
         calibrate_rpn(model, torch.stack([i.to(device) for i in batches[0][0]]))
+        if perturb:
+            assert not patched
+            perturb_roi_align_by_one_ulp(model)
         torch.manual_seed(4321)
         metrics = tc.train_one_epoch(model, _Loader(batches), opt, device, epoch=1)
         val = tc.evaluate(model, _Loader(batches[:1]), device)

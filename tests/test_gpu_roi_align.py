@@ -160,3 +160,49 @@ def test_multilevel_fpn_rois_vs_oracle(ops, oracle, synth, P):
         sel = lv_ref == l
         ref_b = oracle.roi_align_bwd(go[sel], rois[sel], (1, C, h, w), scales[l], 2, False) if sel.any() else np.zeros((1, C, h, w), np.float32)
         assert_close_rel(N(grads[l]), ref_b, RTOL)
+
+
+@pytest.mark.parametrize("C,K,mode,levels", [(256, 600, "anchor", 1), (256, 37, "anchor", 1), (256, 3000, "fpn", 4), (128, 300, "fpn", 1),
+                                              (64, 129, "anchor", 1), (192, 64, "fpn", 2)])
+def test_staged_forward_is_bit_identical_to_the_warp_kernel(ops, synth, oracle, monkeypatch, C, K, mode, levels):
+    """roi_fwd_staged_kernel (window rows staged through shared memory by bulk copies, producer warp + pooling warps)
+    performs the arithmetic of roi_fwd_warp_kernel operation for operation: same bits, for staged RoIs, for the wide RoIs
+    its consumers gather themselves, for padding rows and for every edge case; and both stay within 1e-5 of the oracle."""
+    from gpu_util import N, T, nhwc, assert_close_rel
+    B, H, W = 2, 520, 704
+    rois = synth.make_rois(K, 300 + K, img_h=H, img_w=W, mode=mode, batch=B, edge_cases=True)
+    rois[K // 2, 0] = -1.0                                           # a padding row (batch index -1): zero tile
+    feats, scales = [], []
+    for l in range(levels):
+        h, w = -(-H // (4 << l)), -(-W // (4 << l))
+        feats.append(synth.make_features(B, C, h, w, seed=40 + l))
+        scales.append(1.0 / (4 << l))
+    lv = None
+    if levels > 1:
+        lv = oracle.level_map(rois[:, 1:], 2, 1 + levels, 224.0, 4).astype(np.int32)
+    fd = [nhwc(T(f)) for f in feats]
+    lvd = None if lv is None else T(lv)
+    from livecell_instance_segmentation_b200 import _lib
+    monkeypatch.delenv("LCR_ROI_FWD", raising=False)                 # default dispatch: the warp kernel
+    ref = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
+    monkeypatch.setenv("LCR_ROI_FWD", "staged")
+    got = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
+    assert np.array_equal(got, ref)                                  # 8 pooling warps of 32 channels per CTA
+    monkeypatch.setenv("LCR_ROI_STAGED_WARPS", "4")                  # 4 pooling warps of 64 channels
+    assert np.array_equal(N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False)), ref)
+    monkeypatch.delenv("LCR_ROI_STAGED_WARPS")
+    monkeypatch.setenv("LCR_ROI_FWD", "staged_direct")               # same kernel, nothing staged
+    assert np.array_equal(N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False)), ref)
+    monkeypatch.setenv("LCR_ROI_RPC", "1")
+    monkeypatch.setenv("LCR_ROI_FWD", "staged")
+    assert np.array_equal(N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False)), ref)
+    monkeypatch.setenv("LCR_ROI_RPC", "37")                          # long CTAs: ring wrap-around, descriptor reuse
+    assert np.array_equal(N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False)), ref)
+    if K <= 600:
+        live = rois[:, 0] >= 0
+        if levels == 1:
+            want = oracle.roi_align_fwd(feats[0], rois[live], 7, 7, scales[0], 2, False)
+        else:
+            want = oracle.multiscale_roi_align_fwd(feats, scales, rois[live], lv[live], 7, 7, 2, False)
+        assert_close_rel(got[live], want, RTOL)
+        assert not got[~live].any()

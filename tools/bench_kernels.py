@@ -68,7 +68,7 @@ def main():
         print(json.dumps(kw), flush=True)
 
     def setenv(env):
-        for k in ("LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_PASTE_CTAS", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
+        for k in ("LCR_ROI_RING_KB", "LCR_ROI_STAGED_WARPS", "LCR_ROI_RPC", "LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_PASTE_CTAS", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
                   "LCR_NMS_RESOLVE"):
             os.environ.pop(k, None)
         os.environ.update(env)
@@ -76,9 +76,16 @@ def main():
     if "roi" in only:
         bytes_roi = 4 * n_props * B.C * 49 + F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS
         ref = None
-        for name, env in [("cta(r01)", {"LCR_ROI_FWD": "cta"}), ("warp,persistent", {"LCR_ROI_IPW": "0"}), ("warp,ipw1", {"LCR_ROI_IPW": "1"}),
-                          ("warp,ipw2", {"LCR_ROI_IPW": "2"}), ("warp,ipw2,per-warp tables", {"LCR_ROI_IPW": "2", "LCR_ROI_SHARED_TABLES": "0"}),
-                          ("warp,ipw3", {"LCR_ROI_IPW": "3"}), ("warp,ipw4", {"LCR_ROI_IPW": "4"}),
+        S = {"LCR_ROI_FWD": "staged"}
+        for name, env in [("warp,ipw2 (default)", {}),
+                          ("staged: 8 pooling warps, ring 56 KB (2 CTAs/SM), rpc 8", S),
+                          ("staged: 4 pooling warps, ring 56 KB", {**S, "LCR_ROI_STAGED_WARPS": "4"}),
+                          ("staged: 8 warps, ring 150 KB (1 CTA/SM)", {**S, "LCR_ROI_RING_KB": "150"}),
+                          ("staged: 8 warps, ring 150 KB, rpc 32", {**S, "LCR_ROI_RING_KB": "150", "LCR_ROI_RPC": "32"}),
+                          ("staged: 4 warps, ring 150 KB, rpc 32", {**S, "LCR_ROI_RING_KB": "150", "LCR_ROI_RPC": "32", "LCR_ROI_STAGED_WARPS": "4"}),
+                          ("staged: 8 warps, ring 100 KB, rpc 16", {**S, "LCR_ROI_RING_KB": "100", "LCR_ROI_RPC": "16"}),
+                          ("staged: 8 warps, ring 56 KB, rpc 4", {**S, "LCR_ROI_RPC": "4"}),
+                          ("staged kernel, nothing staged (consumers gather)", {"LCR_ROI_FWD": "staged_direct"}),
                           ("warp,ipw2 (again)", {})]:
             setenv(env)
             out = pipe.pool(feat, props.rois)
@@ -94,6 +101,10 @@ def main():
             del out
         del ref
         setenv({})
+
+    if "roi1" in only:   # the RoIAlign forward selected by the caller's environment, nothing else (ncu target)
+        med, mn = timed(lambda: pipe.pool(feat, props.rois), args.reps, flush)
+        emit(kernel="roi_align_fwd", variant=os.environ.get("LCR_ROI_FWD", "default"), ms=med, ms_min=mn, rois=n_props)
 
     if "roiexp" in only:
         # what bounds the forward kernel?  same launch, different RoI lists (time per item vs window size / locality)

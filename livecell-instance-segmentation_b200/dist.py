@@ -14,12 +14,31 @@ import torch
 import torch.distributed as dist
 
 
+_last_bind_report: dict = {}
+
+
+def last_bind_report() -> dict:
+    """Why the last bind_to_gpu_numa_node() did what it did (for bench.py's e2e line)."""
+    return dict(_last_bind_report)
+
+
 def bind_to_gpu_numa_node(device_index: int) -> list:
     """Pin this process to the CPU cores NVML reports as local to GPU `device_index` (restricted to the cores the
     process may use), so that pinned host buffers are first-touched on the GPU's own NUMA node and the host->device
-    copies of 8 ranks do not cross the socket interconnect.  Returns the core list ([] when nothing was changed)."""
+    copies of 8 ranks do not cross the socket interconnect.  Returns the core list ([] when nothing was changed);
+    last_bind_report() says why."""
     import os
+    rep = {"device_index": device_index, "bound": 0}
+    _last_bind_report.clear()
+    _last_bind_report.update(rep)
     try:
+        allowed = os.sched_getaffinity(0)
+        _last_bind_report["allowed_cores"] = len(allowed)
+        try:
+            nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+            _last_bind_report["numa_nodes"] = len(nodes)
+        except OSError:
+            _last_bind_report["numa_nodes"] = None
         import pynvml
         pynvml.nvmlInit()
         visible = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -32,13 +51,21 @@ def bind_to_gpu_numa_node(device_index: int) -> list:
         ncpu = os.cpu_count() or 1
         words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
         local = {i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1}
-        allowed = os.sched_getaffinity(0)
         cores = sorted(local & allowed)
-        if cores and len(cores) < len(allowed):
+        _last_bind_report["gpu_local_cores"] = len(local)
+        _last_bind_report["gpu_local_and_allowed"] = len(cores)
+        if not cores:
+            _last_bind_report["reason"] = "none of the GPU's local cores is in this process's affinity mask"
+        elif len(cores) >= len(allowed):
+            _last_bind_report["reason"] = ("NVML reports every allowed core as local to this GPU "
+                                           "(single NUMA node / VM without topology): nothing to narrow")
+        else:
             os.sched_setaffinity(0, cores)
+            _last_bind_report["bound"] = len(cores)
+            _last_bind_report["reason"] = "bound to the GPU's local cores"
             return cores
-    except Exception:
-        pass
+    except Exception as exc:  # NVML missing, no permission, ...
+        _last_bind_report["reason"] = f"not attempted: {type(exc).__name__}: {exc}"
     return []
 
 

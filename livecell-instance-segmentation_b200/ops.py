@@ -16,6 +16,7 @@ from ._lib import LcrFeatLevel, LcrRpnCfg, LcrRpnLevel, check
 XFORM_CLIP = math.log(1000.0 / 16)
 
 _workspaces: dict = {}
+_retired: list = []      # outgrown workspaces: kept alive, a CUDA graph captured earlier may still point into them
 
 
 def _stream() -> int:
@@ -66,7 +67,9 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     key = (torch.device(device).index, _stream())
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        if ws is not None:
+            _retired.append(ws)   # never handed back to the allocator: graph replays would otherwise write into foreign memory
+        ws = torch.empty(max(nbytes, 2 * ws.numel() if ws is not None else 0, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
 
@@ -279,15 +282,23 @@ def level_map(boxes: torch.Tensor, k_min: int = 2, k_max: int = 5, canonical_sca
     return lv
 
 
-def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+def to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[N,C,H,W] tensor -> same logical tensor in channels_last memory, through the tiled transpose
-    kernel when a copy is needed (no-op for tensors that already are NHWC-dense)."""
-    _need_cuda(x)
+    kernel when a copy is needed (no-op for tensors that already are NHWC-dense and no `out`).
+    `out`: optional caller-owned channels_last fp32 tensor of the same logical shape (a serving loop reuses it)."""
+    _need_cuda(x, out)
     N, Cc, H, W = x.shape
-    if x.dtype == torch.float32 and x.stride() == (H * W * Cc, 1, W * Cc, Cc):
-        return x
+    nhwc_strides = (H * W * Cc, 1, W * Cc, Cc)
+    if out is not None and (tuple(out.shape) != (N, Cc, H, W) or out.stride() != nhwc_strides or out.dtype != torch.float32):
+        raise _lib.LcrError("to_nhwc: out must be a channels_last fp32 tensor of the input's logical shape")
+    if x.dtype == torch.float32 and x.stride() == nhwc_strides:
+        if out is None:
+            return x
+        out.copy_(x)
+        return out
     xc = _f32c(x)
-    out = torch.empty_strided((N, Cc, H, W), (H * W * Cc, 1, W * Cc, Cc), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty_strided((N, Cc, H, W), nhwc_strides, dtype=torch.float32, device=x.device)
     with _dev(x.device):
         check(_lib.load().lcr_nchw_to_nhwc_f32(xc.data_ptr(), out.data_ptr(), N, Cc, H, W, _stream()), "nchw_to_nhwc")
     return out

@@ -16,7 +16,9 @@ def run(args, env=None):
 
 
 def test_reference_arm_line():
-    res = run(["--impl", "reference", "--steps", "1", "--warmup", "0"])
+    # torchrun exports OMP_NUM_THREADS=1 to every rank (the N >= 2 reference arm ran single-threaded): the arm
+    # must take every usable core anyway
+    res = run(["--impl", "reference", "--steps", "1", "--warmup", "0"], env={"OMP_NUM_THREADS": "1"})
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.strip().startswith("{")]
     assert len(lines) == 1
@@ -25,7 +27,9 @@ def test_reference_arm_line():
     assert d["metric"] == "images_per_sec_rpn_roialign_maskpaste" and d["unit"] == "images/s" and d["value"] > 0
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] == len(os.sched_getaffinity(0)) and cb["value"] == d["value"] and cb["sample"]
+    rp = d["cpu_baseline_reference_python"]          # the unmodified reference functions from baseline/_ref, when staged
+    assert ("unavailable" in rp) or (rp["kind"] == "reference" and rp["value"] > 0 and rp["cores"] >= 1 and rp["value"] < d["value"])
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None
 

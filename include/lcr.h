@@ -160,6 +160,18 @@ int lcr_gather_kept_f32(const float* boxes, const float* scores, const int64_t* 
                         float* out_boxes, float* out_scores, float* out_rois, uint8_t* out_valid,
                         void* stream);
 
+/* a12, cross-level step of torchvision's RPN (TV:models/detection/rpn.py:258-291, TV:ops/boxes.py:51-120).
+ * Input: lcr_rpn_select_f32's per-level outputs boxes [B, L, k, 4], scores [B, L, k], counts [B, L].  Output, per image,
+ * the levels' survivors concatenated in level order: cat_boxes / cat_scores / cat_level [B, L*k] (+ zero / -1 padding)
+ * and cat_counts [B].  nms_boxes (required with coordinate_trick, optional otherwise): the boxes to run NMS on — with
+ * coordinate_trick != 0 each box is offset by level * (max coordinate of the image's boxes + 1) in fp32, as
+ * _batched_nms_coordinate_trick does (torchvision's path up to 1000 boxes per image on CPU / 25 000 on CUDA), so a plain
+ * lcr_nms_f32 over nms_boxes reproduces batched_nms including its rounding; without it pass cat_level as `category`
+ * (_batched_nms_vanilla).  The keep list then indexes cat_boxes (lcr_gather_kept_f32 with post_n = post_nms_top_n). */
+int lcr_rpn_concat_levels_f32(const float* boxes, const float* scores, const int* counts, int B, int L, int k,
+                              int coordinate_trick, float* cat_boxes, float* nms_boxes, float* cat_scores,
+                              int* cat_level, int* cat_counts, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a11. FPN level assignment.  Replaces LevelMapper.__call__ (TV:ops/poolers.py:73-84):
  *   lvl = clamp(floor(lvl0 + log2(sqrt(area)/s0) + eps), k_min, k_max) - k_min       (fp32)
@@ -219,6 +231,15 @@ int lcr_nhwc_to_nchw_f32(const float* in, float* out, int N, int C, int H, int W
  * ---------------------------------------------------------------------------------------------- */
 int lcr_paste_masks_u8(const float* probs, const float* boxes, const uint8_t* valid, int N, int M,
                        int H, int W, float threshold, uint8_t on_value, uint8_t* out, void* stream);
+
+/* a13, torchvision variant (P2).  Replaces torchvision.models.detection.roi_heads.paste_masks_in_image
+ * (TV:models/detection/roi_heads.py:405-501; called by the transfer model's postprocess, src/train_transfer.py:95 ->
+ * RoIHeads.forward -> GeneralizedRCNNTransform.postprocess): zero-pad the M x M probability map by `padding`, expand the box
+ * by (M + 2*padding)/M around its centre, truncate to integers, resize to (y2-y1+1, x2-x1+1) (bilinear,
+ * align_corners=False) and copy the part inside the frame.  out [N, H, W] float32 PROBABILITIES (torchvision returns
+ * [N, 1, H, W]), zero outside the box; no threshold.  valid as in lcr_paste_masks_u8. */
+int lcr_paste_masks_tv_f32(const float* probs, const float* boxes, const uint8_t* valid, int N, int M,
+                           int H, int W, int padding, float* out, void* stream);
 
 /* Detection records for the multi-GPU all-gather: for segment s and slot j,
  * records[s][j] = (x1, y1, x2, y2, score, label) with label = 1.0 for j < counts[s], else all zero.

@@ -15,7 +15,7 @@ import importlib as _importlib
 __version__ = "0.1.0"
 
 _LAZY = {
-    "synth", "build", "_lib", "_ext", "ops", "roi_align", "pipeline", "dist", "install",
+    "synth", "build", "_lib", "_ext", "ops", "roi_align", "pipeline", "dist", "install", "tv_rpn",
 }
 
 

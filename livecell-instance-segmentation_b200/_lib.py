@@ -94,6 +94,10 @@ SIGNATURES = {
     "lcr_nhwc_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "lcr_paste_masks_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                      C.c_uint8, C.c_void_p, C.c_void_p]),
+    "lcr_paste_masks_tv_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p]),
+    "lcr_rpn_concat_levels_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lcr_pack_records_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "lcr_box_iou_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "lcr_box_iou_max_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -122,7 +126,7 @@ def load(build_if_missing: bool = True):
         return _lib
     path = _build.LIB_PATH
     if build_if_missing and _build.is_stale():
-        _build.build()
+        _build.build()          # serialised across processes by a file lock (8 torchrun ranks may arrive here together)
     if not os.path.exists(path):
         raise LcrError(f"{path} is missing: build it with __graft_entry__.build() — there is no CPU fallback")
     lib = C.CDLL(path)

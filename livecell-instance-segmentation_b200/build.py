@@ -51,7 +51,16 @@ def build_torch_ext(force: bool = False, verbose: bool = False) -> str:
     Plain g++ against the installed torch headers; links liblcr.so through an $ORIGIN rpath, in-tree."""
     if not force and not ext_is_stale():
         return EXT_PATH
+    import fcntl
     import sysconfig
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not ext_is_stale():
+            return EXT_PATH
+        return _build_torch_ext_locked(verbose, sysconfig)
+
+
+def _build_torch_ext_locked(verbose, sysconfig) -> str:
 
     import torch
     tdir = os.path.dirname(torch.__file__)
@@ -94,6 +103,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
+    import fcntl
+    lock = open(os.path.join(CSRC, ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)       # ranks started together (torchrun) build once, the others wait and find it fresh
+    try:
+        if not force and not is_stale():
+            return LIB_PATH
+        return _build_locked(nvcc, force, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc: str, force: bool, verbose: bool) -> str:
     header_time = max(os.path.getmtime(os.path.join(CSRC, "common.cuh")), os.path.getmtime(os.path.join(INCLUDE, "lcr.h")))
 
     def compile_one(src: str) -> str:

@@ -114,6 +114,72 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const float4* __restr
   }
 }
 
+// Cross-level concatenation for torchvision's RPN (a12; TV:models/detection/rpn.py:258-291, TV:ops/boxes.py:51-120): the
+// per-level survivors of lcr_rpn_select_f32 ([B, L, k] padded, counts [B, L]) become one list per image in level order
+// (the order filter_proposals sees after its top-n gather and order-preserving filters), with the level id of every box.
+// With `trick` the boxes handed to NMS are offset by level * (max coordinate of the image's boxes + 1), exactly as
+// _batched_nms_coordinate_trick does (each torch op one fp32 rounding): NMS over the offset boxes then needs no
+// category test — and reproduces torchvision's rounding of the shifted coordinates.
+__global__ void __launch_bounds__(256) concat_levels_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                                                             const int* __restrict__ counts, int L, int k, int trick,
+                                                             float4* __restrict__ cat_boxes, float4* __restrict__ nms_boxes,
+                                                             float* __restrict__ cat_scores, int* __restrict__ cat_level,
+                                                             int* __restrict__ cat_counts) {
+  const int b = blockIdx.x;
+  __shared__ int s_off[LCR_MAX_LEVELS + 1];
+  __shared__ float s_max[8];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int l = 0; l < L; ++l) {
+      s_off[l] = acc;
+      acc += min(max(counts[b * L + l], 0), k);
+    }
+    s_off[L] = acc;
+    cat_counts[b] = acc;
+  }
+  __syncthreads();
+  const int total = s_off[L];
+  float shift = 0.f;
+  if (trick) {   // boxes.max() over the image's boxes (NaN ignored: fmaxf)
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < L * k; j += blockDim.x) {
+      const int l = j / k, r = j - l * k;
+      if (r < s_off[l + 1] - s_off[l]) {
+        const float4 v = __ldg(boxes + ((size_t)b * L + l) * k + r);
+        m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = s_max[0];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_max[w]);
+    shift = __fadd_rn(m, 1.0f);
+  }
+  for (int j = threadIdx.x; j < L * k; j += blockDim.x) {
+    const int l = j / k, r = j - l * k;
+    const size_t dst = (size_t)b * L * k + s_off[l] + r;
+    if (r < s_off[l + 1] - s_off[l]) {
+      const size_t src = ((size_t)b * L + l) * k + r;
+      const float4 v = __ldg(boxes + src);
+      cat_boxes[dst] = v;
+      cat_scores[dst] = __ldg(scores + src);
+      cat_level[dst] = l;
+      if (nms_boxes) {
+        const float o = __fmul_rn((float)l, shift);   // idxs.to(boxes) * (max_coordinate + 1)
+        nms_boxes[dst] = trick ? make_float4(__fadd_rn(v.x, o), __fadd_rn(v.y, o), __fadd_rn(v.z, o), __fadd_rn(v.w, o)) : v;
+      }
+    }
+  }
+  for (int j = total + threadIdx.x; j < L * k; j += blockDim.x) {   // padding rows
+    const size_t dst = (size_t)b * L * k + j;
+    cat_boxes[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cat_scores[dst] = 0.f;
+    cat_level[dst] = -1;
+    if (nms_boxes) nms_boxes[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 }  // namespace lcr
 
 using namespace lcr;
@@ -195,5 +261,20 @@ extern "C" int lcr_pack_records_f32(const float* boxes, const float* scores, con
   const int n = S * stride;
   pack_records_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(boxes), scores, counts,
                                                                      S, stride, records);
+  return after_launch();
+}
+
+extern "C" int lcr_rpn_concat_levels_f32(const float* boxes, const float* scores, const int* counts, int B, int L, int k,
+                                         int coordinate_trick, float* cat_boxes, float* nms_boxes, float* cat_scores,
+                                         int* cat_level, int* cat_counts, void* stream) {
+  LCR_REQUIRE(B >= 0 && L > 0 && k > 0, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(L <= LCR_MAX_LEVELS, LCR_ERR_CAPACITY);
+  if (B == 0) return LCR_OK;
+  LCR_REQUIRE(boxes && scores && counts && cat_boxes && cat_scores && cat_level && cat_counts, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(!coordinate_trick || nms_boxes, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(aligned_to(boxes, 16) && aligned_to(cat_boxes, 16) && (!nms_boxes || aligned_to(nms_boxes, 16)), LCR_ERR_ALIGNMENT);
+  concat_levels_kernel<<<B, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(boxes), scores, counts, L, k,
+                                                        coordinate_trick ? 1 : 0, reinterpret_cast<float4*>(cat_boxes),
+                                                        reinterpret_cast<float4*>(nms_boxes), cat_scores, cat_level, cat_counts);
   return after_launch();
 }

@@ -384,6 +384,84 @@ __global__ void __launch_bounds__(256) paste_generic_kernel(const float* __restr
   }
 }
 
+// ---- torchvision-style paste (a13, P2 variant) --------------------------------------------------------------------------
+// torchvision.models.detection.roi_heads.paste_masks_in_image (TV:models/detection/roi_heads.py:405-501), what the transfer
+// model's postprocess runs: the M x M PROBABILITY map is zero-padded by `padding` pixels, the box is expanded by
+// (M + 2*padding) / M around its centre and truncated to integers, the padded map is resized (bilinear, align_corners=False)
+// to (y2 - y1 + 1, x2 - x1 + 1) and the part inside the frame is copied: float32 frames, no threshold.
+// One CTA per (detection, band of rows); a thread owns four consecutive pixels of a row and stores one float4, so the frame
+// (4 B/pixel: 1.46 MB per detection at 704x520) is written as full lines.  HBM-write-bound.
+struct TvBox {
+  int x0, y0, w, h;   // integer expanded box origin and resized extents (>= 1)
+  int xe, ye;         // box[2] + 1, box[3] + 1: exclusive end of the pasted region (<= origin for an inverted box: nothing pasted)
+};
+
+__device__ __forceinline__ TvBox tv_box(const float* __restrict__ b, float scale) {
+  // expand_boxes: every torch op is one fp32 rounding
+  const float x1 = __ldg(b), y1 = __ldg(b + 1), x2 = __ldg(b + 2), y2 = __ldg(b + 3);
+  const float wh = __fmul_rn(__fmul_rn(__fsub_rn(x2, x1), 0.5f), scale), hh = __fmul_rn(__fmul_rn(__fsub_rn(y2, y1), 0.5f), scale);
+  const float xc = __fmul_rn(__fadd_rn(x2, x1), 0.5f), yc = __fmul_rn(__fadd_rn(y2, y1), 0.5f);
+  const long long ex0 = (long long)__fsub_rn(xc, wh), ex1 = (long long)__fadd_rn(xc, wh);   // .to(torch.int64): truncation
+  const long long ey0 = (long long)__fsub_rn(yc, hh), ey1 = (long long)__fadd_rn(yc, hh);
+  TvBox t;
+  t.x0 = (int)max(min(ex0, (long long)(1 << 29)), -(long long)(1 << 29));
+  t.y0 = (int)max(min(ey0, (long long)(1 << 29)), -(long long)(1 << 29));
+  const long long w = ex1 - ex0 + 1, h = ey1 - ey0 + 1;
+  t.w = (int)max(min(w, (long long)(1 << 29)), 1ll);
+  t.h = (int)max(min(h, (long long)(1 << 29)), 1ll);
+  t.xe = (int)max(min(ex1 + 1, (long long)(1 << 29)), -(long long)(1 << 29));
+  t.ye = (int)max(min(ey1 + 1, (long long)(1 << 29)), -(long long)(1 << 29));
+  return t;
+}
+
+__global__ void __launch_bounds__(256) paste_tv_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
+                                                       const uint8_t* __restrict__ valid, int M, int H, int W, int pad, float scale,
+                                                       int band_rows, float* __restrict__ out) {
+  const int i = blockIdx.y;
+  if (valid && !valid[i]) return;
+  extern __shared__ float sprob[];   // the padded map, (M + 2 pad)^2
+  const int Mp = M + 2 * pad;
+  for (int j = threadIdx.x; j < Mp * Mp; j += blockDim.x) {
+    const int y = j / Mp - pad, x = j % Mp - pad;
+    sprob[j] = (y >= 0 && y < M && x >= 0 && x < M) ? __ldg(probs + (size_t)i * M * M + y * M + x) : 0.f;
+  }
+  __syncthreads();
+  const TvBox tb = tv_box(boxes + (size_t)i * 4, scale);
+  const float sh = __fdiv_rn((float)Mp, (float)tb.h), sw = __fdiv_rn((float)Mp, (float)tb.w);
+  // region copied into the frame: [max(y0, 0), min(box[3] + 1, H)) x [max(x0, 0), min(box[2] + 1, W))
+  const int ya = max(tb.y0, 0), yb = min(tb.ye, H), xa = max(tb.x0, 0), xb = min(tb.xe, W);
+  float* frame = out + (size_t)i * H * W;
+  const int row0 = blockIdx.x * band_rows, row1 = min(H, row0 + band_rows);
+  const int vpr = (W + 3) / 4;
+  for (int idx = threadIdx.x; idx < (row1 - row0) * vpr; idx += blockDim.x) {
+    const int y = row0 + idx / vpr, xq = (idx % vpr) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (y >= ya && y < yb && xq + 3 >= xa && xq < xb) {
+      int h0, h1;
+      float wy0, wy1;
+      src_index(sh, y - tb.y0, Mp, h0, h1, wy0, wy1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int x = xq + q;
+        if (x >= xa && x < xb) {
+          int w0, w1;
+          float wx0, wx1;
+          src_index(sw, x - tb.x0, Mp, w0, w1, wx0, wx1);
+          const float top = __fmaf_rn(sprob[h0 * Mp + w0], wx0, __fmul_rn(sprob[h0 * Mp + w1], wx1));
+          const float bot = __fmaf_rn(sprob[h1 * Mp + w0], wx0, __fmul_rn(sprob[h1 * Mp + w1], wx1));
+          v[q] = __fmaf_rn(top, wy0, __fmul_rn(bot, wy1));
+        }
+      }
+    }
+    float* dst = frame + (size_t)y * W + xq;
+    if (xq + 3 < W && (W % 4 == 0)) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      for (int q = 0; q < 4 && xq + q < W; ++q) dst[q] = v[q];
+    }
+  }
+}
+
 static int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
 
 }  // namespace lcr
@@ -475,5 +553,23 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
   LCR_REQUIRE(N <= 65535, LCR_ERR_CAPACITY);
   dim3 grid((unsigned)((H * W + 255) / 256 < 64 ? (H * W + 255) / 256 : 64), (unsigned)N);
   paste_generic_kernel<<<grid, 256, 0, as_stream(stream)>>>(probs, boxes, valid, N, M, H, W, threshold, on_value, out);
+  return after_launch();
+}
+
+extern "C" int lcr_paste_masks_tv_f32(const float* probs, const float* boxes, const uint8_t* valid, int N, int M, int H, int W,
+                                      int padding, float* out, void* stream) {
+  LCR_REQUIRE(N >= 0 && M > 0 && H > 0 && W > 0 && padding >= 0 && padding <= 8, LCR_ERR_INVALID_ARG);
+  if (N == 0) return LCR_OK;
+  LCR_REQUIRE(probs && boxes && out, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(aligned_to(out, 16), LCR_ERR_ALIGNMENT);
+  LCR_REQUIRE(N <= 65535 && (int64_t)H * W < (1ll << 31), LCR_ERR_CAPACITY);
+  const int Mp = M + 2 * padding;
+  const size_t smem = sizeof(float) * (size_t)Mp * Mp;
+  LCR_REQUIRE(smem <= 48 * 1024, LCR_ERR_CAPACITY);
+  // scale = float(M + 2 * padding) / M as a Python float, applied to a float32 tensor: rounded to fp32 first
+  const float scale = (float)((double)Mp / (double)M);
+  const int band_rows = 32;
+  dim3 grid((unsigned)((H + band_rows - 1) / band_rows), (unsigned)N);
+  paste_tv_kernel<<<grid, 256, smem, as_stream(stream)>>>(probs, boxes, valid, M, H, W, padding, scale, band_rows, out);
   return after_launch();
 }

@@ -401,6 +401,47 @@ def paste_masks(probs: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int
     return out
 
 
+def paste_masks_tv(probs: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int, padding: int = 1,
+                   valid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a13, torchvision variant — torchvision.models.detection.roi_heads.paste_masks_in_image (TV:models/detection/
+    roi_heads.py:405-501): probs [N,M,M] (or [N,1,M,M]) f32, boxes [N,4] -> float32 [N,1,H,W] probabilities pasted into
+    the box expanded by (M + 2 padding)/M, zero elsewhere."""
+    _need_cuda(probs, boxes, valid, out)
+    p, b = _f32c(probs), _f32c(boxes).reshape(-1, 4)
+    N = b.shape[0]
+    M = p.shape[-1] if p.numel() else 28
+    if out is None:
+        out = torch.empty((N, 1, img_h, img_w), dtype=torch.float32, device=b.device)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() < N * img_h * img_w:
+        raise _lib.LcrError("paste_masks_tv: out must be a contiguous float32 buffer of at least N*H*W elements")
+    v = None if valid is None else valid.to(torch.uint8).contiguous()
+    if N:
+        with _dev(b.device):
+            check(_lib.load().lcr_paste_masks_tv_f32(p.data_ptr(), b.data_ptr(), _ptr(v), N, M, img_h, img_w, int(padding),
+                                                     out.data_ptr(), _stream()), "paste_masks_tv")
+    return out
+
+
+def rpn_concat_levels(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor, coordinate_trick: bool):
+    """a12 — the cross-level step of torchvision's RPN (see lcr_rpn_concat_levels_f32): boxes [B,L,k,4], scores [B,L,k],
+    counts [B,L] -> (cat_boxes [B,L*k,4], nms_boxes [B,L*k,4], cat_scores [B,L*k], cat_level [B,L*k] i32, cat_counts [B])."""
+    _need_cuda(boxes, scores, counts)
+    b, s = _f32c(boxes), _f32c(scores)
+    B, L, k = s.shape
+    cn = counts.to(torch.int32).contiguous()
+    cb = torch.empty((B, L * k, 4), dtype=torch.float32, device=b.device)
+    nb = torch.empty((B, L * k, 4), dtype=torch.float32, device=b.device)
+    cs = torch.empty((B, L * k), dtype=torch.float32, device=b.device)
+    cl = torch.empty((B, L * k), dtype=torch.int32, device=b.device)
+    cc = torch.empty((B,), dtype=torch.int32, device=b.device)
+    if B:
+        with _dev(b.device):
+            check(_lib.load().lcr_rpn_concat_levels_f32(b.data_ptr(), s.data_ptr(), cn.data_ptr(), B, L, k, 1 if coordinate_trick else 0,
+                                                        cb.data_ptr(), nb.data_ptr(), cs.data_ptr(), cl.data_ptr(), cc.data_ptr(),
+                                                        _stream()), "rpn_concat_levels")
+    return cb, nb, cs, cl, cc
+
+
 def pack_records(boxes: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
     """Detection records [S, stride, 6] = (x1,y1,x2,y2,score,label=1), zero padded."""
     _need_cuda(boxes, scores, counts)

@@ -446,6 +446,50 @@ void orc_paste_masks(const float* probs, const float* boxes, const uint8_t* vali
   }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * torchvision's paste (a13, P2 variant) — paste_masks_in_image / expand_masks / expand_boxes / paste_mask_in_image,
+ * TV:models/detection/roi_heads.py:405-501.  scale = float(M + 2 pad) / M is a Python float multiplied into a float32
+ * tensor (rounded to fp32); boxes_exp.to(int64) truncates; w = max(int(x2 - x1 + 1), 1); the padded map is resized with
+ * ATen's bilinear (same src_index / FMA placement as above); the frame receives
+ * mask[(y_0 - y1):(y_1 - y1), (x_0 - x1):(x_1 - x1)] with x_0 = max(x1, 0), x_1 = min(x2 + 1, W).
+ * Boxes that lie entirely outside the frame leave it zero (torchvision's negative slice bounds would wrap around; its
+ * callers clip boxes to the image first).  out [N, H, W] float32.
+ * ------------------------------------------------------------------------------------------- */
+void orc_paste_masks_tv(const float* probs, const float* boxes, int N, int M, int H, int W, int pad, float* out) {
+  const int Mp = M + 2 * pad;
+  const float scale = (float)((double)Mp / (double)M);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < N; ++i) {
+    float* frame = out + (size_t)i * H * W;
+    memset(frame, 0, sizeof(float) * (size_t)H * W);
+    float* pm = (float*)calloc((size_t)Mp * Mp, sizeof(float));
+    for (int y = 0; y < M; ++y)
+      for (int x = 0; x < M; ++x) pm[(y + pad) * Mp + (x + pad)] = probs[(size_t)i * M * M + y * M + x];
+    const float* b = boxes + (size_t)i * 4;
+    const float wh = ((b[2] - b[0]) * 0.5f) * scale, hh = ((b[3] - b[1]) * 0.5f) * scale;
+    const float xc = (b[2] + b[0]) * 0.5f, yc = (b[3] + b[1]) * 0.5f;
+    const long long x1 = (long long)(xc - wh), x2 = (long long)(xc + wh), y1 = (long long)(yc - hh), y2 = (long long)(yc + hh);
+    long long w = x2 - x1 + 1, h = y2 - y1 + 1;
+    if (w < 1) w = 1;
+    if (h < 1) h = 1;
+    const float sh = (float)Mp / (float)h, sw = (float)Mp / (float)w;
+    const long long xa = x1 > 0 ? x1 : 0, xb = (x2 + 1 < W) ? x2 + 1 : W;   /* x_1 = min(box[2] + 1, im_w): empty for x2 < x1 */
+    const long long ya = y1 > 0 ? y1 : 0, yb = (y2 + 1 < H) ? y2 + 1 : H;
+    for (long long y = ya; y < yb; ++y) {
+      int h0, h1; float wy0, wy1;
+      src_index(sh, (int)(y - y1), Mp, &h0, &h1, &wy0, &wy1);
+      for (long long x = xa; x < xb; ++x) {
+        int w0, w1; float wx0, wx1;
+        src_index(sw, (int)(x - x1), Mp, &w0, &w1, &wx0, &wx1);
+        const float r0 = fmaf(pm[h0 * Mp + w0], wx0, pm[h0 * Mp + w1] * wx1);
+        const float r1 = fmaf(pm[h1 * Mp + w0], wx0, pm[h1 * Mp + w1] * wx1);
+        frame[(size_t)y * W + x] = fmaf(r0, wy0, r1 * wy1);
+      }
+    }
+    free(pm);
+  }
+}
+
 /* Detection records (x1,y1,x2,y2,score,label=1) padded with zeros — SURVEY.md §8(e);
  * labels = ones per src/custom_maskrcnn.py:204. */
 void orc_pack_records(const float* boxes, const float* scores, const int* counts, int S, int stride,

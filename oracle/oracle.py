@@ -243,6 +243,65 @@ def paste_masks(probs, boxes, H, W, thr=0.5, on_value=255, valid=None, out=None)
     return out
 
 
+def paste_masks_tv(probs, boxes, H, W, padding=1) -> np.ndarray:
+    """torchvision's paste_masks_in_image (TV:models/detection/roi_heads.py:405-501) -> float32 [N,H,W] probabilities."""
+    p = _f32(probs)
+    N, M = p.shape[0], p.shape[-1]
+    b = _f32(boxes).reshape(-1, 4)
+    out = np.zeros((N, H, W), np.float32)
+    lib().orc_paste_masks_tv(_p(p), _p(b), C.c_int(N), C.c_int(M), C.c_int(H), C.c_int(W), C.c_int(padding), _p(out))
+    return out
+
+
+def tv_base_anchors(sizes, aspect_ratios) -> np.ndarray:
+    """torchvision AnchorGenerator.generate_anchors (TV:models/detection/anchor_utils.py:58-78): ratio = h/w,
+    h_ratios = sqrt(ratios), w_ratios = 1/h_ratios, all in fp32, base = round([-w,-h,w,h]/2) (half to even)."""
+    scales = np.asarray(sizes, np.float32)
+    ratios = np.asarray(aspect_ratios, np.float32)
+    h_r = np.sqrt(ratios)
+    w_r = (np.float32(1.0) / h_r).astype(np.float32)
+    ws = (w_r[:, None] * scales[None, :]).reshape(-1)
+    hs = (h_r[:, None] * scales[None, :]).reshape(-1)
+    base = (np.stack([-ws, -hs, ws, hs], axis=1) / np.float32(2.0)).astype(np.float32)
+    return np.round(base).astype(np.float32)
+
+
+def tv_rpn_filter_proposals(objs, deltas, bases, strides, img_h, img_w, *, k, post_n, nms_thresh, score_thresh=0.0,
+                            min_size=1e-3, coordinate_trick=None):
+    """torchvision RegionProposalNetwork.forward's inference path for ONE image (TV:models/detection/rpn.py:231-297,
+    :339-367): per level top-k on the LOGITS, decode (BoxCoder weights 1,1,1,1), sigmoid, clip, remove_small_boxes(min_size),
+    `score >= score_thresh`, batched_nms over the levels, first post_n.
+    objs / deltas: per-level [A,h,w] / [4A,h,w]; bases: per-level [A,4] (tv_base_anchors).  coordinate_trick: None = what
+    torchvision does on CPU (trick iff 4 * boxes <= 4000), True/False to force.
+    Returns (boxes [n,4], scores [n], level [n], top_idx: per-level flat indices of the pre-NMS top-k)."""
+    cb, cs, cl, top = [], [], [], []
+    for l, (o, d) in enumerate(zip(objs, deltas)):
+        n = int(np.prod(o.shape))
+        kk = min(k, n)
+        # the unfiltered top-k index list (what _get_top_n_idx returns)
+        _, _, ti = rpn_select(o, base=bases[l], stride=strides[l], k=kk, score_thresh=-1.0, score_strict=False, min_size=-1.0,
+                              img_h=img_h, img_w=img_w, topk_on_sigmoid=False, deltas=d)
+        top.append(ti)
+        b, s, _ = rpn_select(o, base=bases[l], stride=strides[l], k=kk, score_thresh=score_thresh, score_strict=False,
+                             min_size=min_size, img_h=img_h, img_w=img_w, topk_on_sigmoid=False, deltas=d)
+        cb.append(b)
+        cs.append(s)
+        cl.append(np.full((len(s),), l, np.int32))
+    boxes, scores, level = np.concatenate(cb), np.concatenate(cs), np.concatenate(cl)
+    if coordinate_trick is None:
+        coordinate_trick = boxes.size <= 4000
+    if len(boxes) == 0:
+        return boxes, scores, level, top
+    if coordinate_trick:          # _batched_nms_coordinate_trick: fp32 offsets, plain nms
+        shift = np.float32(boxes.max()) + np.float32(1.0)
+        off = (level.astype(np.float32) * shift).astype(np.float32)
+        keep = nms((boxes + off[:, None]).astype(np.float32), scores, nms_thresh)
+    else:                         # _batched_nms_vanilla: per-level nms, result sorted by score
+        keep = nms(boxes, scores, nms_thresh, category=level)
+    keep = keep[:post_n]
+    return boxes[keep], scores[keep], level[keep], top
+
+
 def pack_records(boxes, scores, counts) -> np.ndarray:
     b, s = _f32(boxes), _f32(scores)
     S, stride = s.shape

@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
+sys.path.insert(0, HERE)
 
 from livecell_instance_segmentation_b200 import synth  # noqa: E402
 
@@ -304,7 +305,101 @@ def gen_tail_stitch():
     save("tail_stitch", **out)
 
 
+
+from tv_cases import tv_rpn_case  # noqa: E402  (seeded inputs shared with the tests)
+
+
+def gen_tv_rpn():
+    """a12 — torchvision's own RegionProposalNetwork (TV:models/detection/rpn.py:231-297 filter_proposals / _get_top_n_idx,
+    :339-367 forward) with torchvision's AnchorGenerator (TV:models/detection/anchor_utils.py:58-133: ratio = h/w, rounded
+    base anchors), BoxCoder.decode and batched_nms, executed on CPU.  The head is a stand-in that returns the seeded
+    objectness / delta maps, everything after it is torchvision's code."""
+    from torchvision.models.detection.anchor_utils import AnchorGenerator as TVAnchorGenerator
+    from torchvision.models.detection.image_list import ImageList
+    from torchvision.models.detection.rpn import RegionProposalNetwork
+
+    class Head(torch.nn.Module):
+        def __init__(self, obj, deltas):
+            super().__init__()
+            self.obj, self.deltas = obj, deltas
+
+        def forward(self, features):
+            return [T(o) for o in self.obj], [T(d) for d in self.deltas]
+
+    out = {}
+    for tag in ("trick", "vanilla"):
+        c = tv_rpn_case(tag)
+        L, B = len(c["sizes"]), c["B"]
+        ag = TVAnchorGenerator(sizes=c["sizes"], aspect_ratios=(c["ratios"],) * L)
+        rpn = RegionProposalNetwork(ag, Head(c["obj"], c["deltas"]), fg_iou_thresh=0.7, bg_iou_thresh=0.3, batch_size_per_image=256,
+                                    positive_fraction=0.5, pre_nms_top_n=dict(training=c["k"], testing=c["k"]),
+                                    post_nms_top_n=dict(training=c["post"], testing=c["post"]), nms_thresh=c["nms"],
+                                    score_thresh=c["score_thresh"])
+        rpn.min_size = c["min_size"]
+        rpn.eval()
+        images = ImageList(torch.zeros((B, 3, c["H"], c["W"])), [(c["H"], c["W"])] * B)
+        feats = {str(l): torch.zeros((B, 8, h, w)) for l, (h, w) in enumerate(c["shapes"])}
+        captured = {}
+        inner = rpn.filter_proposals
+
+        def spy(proposals, objectness, image_shapes, num_anchors_per_level):
+            captured["proposals"] = proposals.clone()
+            captured["top_n_idx"] = rpn._get_top_n_idx(objectness.detach().reshape(B, -1), num_anchors_per_level)
+            captured["n_per_level"] = list(num_anchors_per_level)
+            return inner(proposals, objectness, image_shapes, num_anchors_per_level)
+
+        rpn.filter_proposals = spy
+        with torch.no_grad():
+            boxes, _ = rpn(images, feats)
+        # scores are not returned by forward(): recompute them exactly as filter_proposals does
+        with torch.no_grad():
+            fb, fs = inner(captured["proposals"], torch.cat([T(o).permute(0, 2, 3, 1).reshape(B, -1) for o in c["obj"]], dim=1).reshape(-1, 1),
+                           images.image_sizes, captured["n_per_level"])
+        anchors = ag(images, list(feats.values()))[0].numpy()
+        numel = [int(min(c["k"], n)) for n in captured["n_per_level"]]
+        out[f"{tag}_anchors_sha256"] = sha(anchors)
+        out[f"{tag}_anchor_rows"] = anchors[[0, 1, 2, 3, anchors.shape[0] // 2, anchors.shape[0] - 1]]
+        out[f"{tag}_base_anchors"] = np.stack([b.numpy() for b in ag.cell_anchors])
+        out[f"{tag}_top_n_idx"] = captured["top_n_idx"].numpy().astype(np.int32)          # [B, sum_l min(k, n_l)], level offsets included
+        out[f"{tag}_pre_nms_per_level"] = np.array(numel)
+        out[f"{tag}_uses_coordinate_trick"] = np.array(sum(numel) * 4 <= 4000)
+        for b in range(B):
+            assert torch.equal(boxes[b], fb[b])
+            s = fs[b].numpy()
+            assert np.unique(s).size == s.size, "cross-level score tie in the fixture: change the seed"
+            out[f"{tag}_boxes_{b}"], out[f"{tag}_scores_{b}"] = boxes[b].numpy(), s
+        print(f"tv_rpn[{tag}]: {[len(b) for b in boxes]} proposals, coordinate trick: {bool(out[f'{tag}_uses_coordinate_trick'])}")
+    save("tv_rpn", **out)
+
+
+def gen_tv_paste():
+    """a13, P2 variant — torchvision's paste_masks_in_image (TV:models/detection/roi_heads.py:405-501): boxes expanded by
+    (M + 2) / M with the mask zero-padded by 1 px, integer box with +1 extents (TO_REMOVE = 1), bilinear resize of the
+    PROBABILITIES (align_corners=False), float32 result [N, 1, H, W] (no threshold)."""
+    from torchvision.models.detection.roi_heads import paste_masks_in_image as tv_paste
+    rng = np.random.RandomState(77)
+    out = {}
+    for tag, (H, W, N_) in {"a": (96, 128, 24), "b": (222, 300, 12)}.items():
+        probs = synth.make_mask_probs(N_, 28, 300 + H)
+        w = rng.uniform(4, 70, N_)
+        h = rng.uniform(4, 70, N_)
+        x1 = rng.uniform(-10, W - 8, N_)
+        y1 = rng.uniform(-10, H - 8, N_)
+        boxes = np.stack([x1, y1, x1 + w, y1 + h], 1).astype(np.float32)
+        boxes[0] = [10.2, 12.7, 10.9, 40.3]             # narrower than a pixel
+        boxes[1] = [-20.0, -15.0, W + 30.0, H + 25.0]   # larger than the frame
+        boxes[2] = [W - 3.5, H - 2.5, W + 20.0, H + 20.0]
+        res = tv_paste(T(probs)[:, None], T(boxes), (H, W), padding=1)
+        out[f"{tag}_probs"], out[f"{tag}_boxes"], out[f"{tag}_out"] = probs, boxes, res.numpy()[:, 0]
+        out[f"{tag}_size"] = np.array([H, W])
+    save("tv_paste", **out)
+
+
 if __name__ == "__main__":
+    if "--only-tv" in sys.argv:
+        gen_tv_rpn()
+        gen_tv_paste()
+        sys.exit(0)
     if "--only-match" in sys.argv:
         gen_match()
         sys.exit(0)
@@ -320,3 +415,5 @@ if __name__ == "__main__":
     gen_pipeline()
     gen_match()
     gen_tail_stitch()
+    gen_tv_rpn()
+    gen_tv_paste()

@@ -228,3 +228,57 @@ def test_tail_and_stitch_rows_golden(oracle, golden):
     assert np.array_equal(np.array([k[1] for k in kept]), g["kept_fraction"])          # float64, same summation order
     assert np.array_equal(np.array([k[2] for k in kept]), g["kept_score"])
     np.testing.assert_allclose(np.array([k[3] for k in kept]), g["kept_box"], rtol=0, atol=1e-4)
+
+
+# ---- a12 / a13 (P2): torchvision's own RegionProposalNetwork and paste_masks_in_image ------------------------------------------
+def _tv_case(tag):
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_golden_cases", os.path.join(os.path.dirname(__file__), "golden", "tv_cases.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.tv_rpn_case(tag)
+
+
+@pytest.mark.parametrize("tag", ["trick", "vanilla"])
+def test_torchvision_rpn_filter_proposals(oracle, golden, tag):
+    """tests/golden/tv_rpn.npz = outputs of torchvision's RegionProposalNetwork.forward (eval) with torchvision's
+    AnchorGenerator, BoxCoder and batched_nms on seeded objectness / delta maps (make_golden.py:gen_tv_rpn).  The oracle's
+    restatement must reproduce: the anchors (sha256 of all of them), the per-level top-n index lists bit-exactly, and the final
+    proposals — same boxes (decode: 1e-5 relative, exp), scores 1e-6, in the same order."""
+    import hashlib
+    g = golden("tv_rpn")
+    c = _tv_case(tag)
+    L = len(c["sizes"])
+    bases = [oracle.tv_base_anchors(c["sizes"][l], c["ratios"]) for l in range(L)]
+    assert np.array_equal(np.stack(bases), g[f"{tag}_base_anchors"])
+    anchors = np.concatenate([oracle.anchors(h, w, c["strides"][l], bases[l]) for l, (h, w) in enumerate(c["shapes"])])
+    assert np.array_equal(np.frombuffer(hashlib.sha256(anchors.tobytes()).digest(), np.uint8), g[f"{tag}_anchors_sha256"])
+    trick = bool(g[f"{tag}_uses_coordinate_trick"])
+    for b in range(c["B"]):
+        boxes, scores, level, top = oracle.tv_rpn_filter_proposals(
+            [o[b] for o in c["obj"]], [d[b] for d in c["deltas"]], bases, c["strides"], c["H"], c["W"], k=c["k"], post_n=c["post"],
+            nms_thresh=c["nms"], score_thresh=c["score_thresh"], min_size=c["min_size"], coordinate_trick=trick)
+        off, want_idx = 0, g[f"{tag}_top_n_idx"][b]
+        pos = 0
+        for l, (h, w) in enumerate(c["shapes"]):
+            n = len(top[l])
+            assert np.array_equal(top[l] + off, want_idx[pos:pos + n]), (tag, b, l)        # bit-exact top-n indices
+            pos += n
+            off += c["A"] * h * w
+        assert pos == want_idx.size
+        wb, ws = g[f"{tag}_boxes_{b}"], g[f"{tag}_scores_{b}"]
+        assert len(boxes) == len(wb), (tag, b, len(boxes), len(wb))
+        np.testing.assert_allclose(scores, ws, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(boxes, wb, rtol=1e-5, atol=1e-4)
+
+
+def test_torchvision_paste_masks(oracle, golden):
+    """tests/golden/tv_paste.npz = torchvision.models.detection.roi_heads.paste_masks_in_image(padding=1) on CPU."""
+    g = golden("tv_paste")
+    for tag in ("a", "b"):
+        H, W = [int(v) for v in g[f"{tag}_size"]]
+        out = oracle.paste_masks_tv(g[f"{tag}_probs"], g[f"{tag}_boxes"], H, W, padding=1)
+        want = g[f"{tag}_out"]
+        assert np.array_equal(out != 0, want != 0)                   # the same pixels are written
+        np.testing.assert_allclose(out, want, rtol=0, atol=1e-6)     # ATen's CPU bilinear is FMA-contracted per build

@@ -53,6 +53,11 @@ int lcr_last_cuda_error(void);
 /* Number of kernels launched by this library in this process (monotonic; for bench.py's gpu_launches). */
 uint64_t lcr_launch_count(void);
 
+/* Tuning switches (LCR_ROI_FWD, LCR_PASTE, LCR_SELECT, LCR_NMS_RESOLVE, ...: the alternative kernels kept for A/B runs and
+ * tests, listed in DESIGN.md).  The process environment is read once, on first use; this call overrides a switch at run time
+ * (value == NULL: back to the default).  Results never depend on a switch, only which kernel produces them. */
+int lcr_set_tuning(const char* key, const char* value);
+
 /* ------------------------------------------------------------------------------------------------
  * a1. Anchors.  Replaces AnchorGenerator.generate_anchors (src/components/anchor_generator.py:13-37).
  * out[(y*w + x)*A + a] = fp32(x*stride, y*stride, x*stride, y*stride) + base[a]   (one fp32 add)
@@ -189,13 +194,16 @@ int lcr_level_map_f32(const float* boxes, int box_stride, int K, int k_min, int 
  * and, with L > 1 and roi_level given, MultiScaleRoIAlign (TV:ops/poolers.py:147-227).
  *
  * Each level is a [N, C, H, W] fp32 tensor addressed through ELEMENT strides, so both NCHW and
- * channels_last (NHWC memory) maps are accepted.  The warp-item fast path (TMA bulk store of the pooled tile) needs sc == 1 (NHWC),
- * C % 64 == 0 and 16-byte aligned rows; every other layout runs the generic kernel.
- * rois [K,5] = (batch_idx as float, x1, y1, x2, y2) (TV:ops/_utils.py:18-25).  A roi with
- * batch_idx < 0 is padding: forward writes zeros for it, backward ignores it.
- * roi_level [K] i32 or NULL (all rois on level 0).  out / grad_out: [K, C, PH, PW] contiguous.
- * Backward accumulates into grad levels with the same shapes/strides as the forward features;
- * when zero_grad != 0 the callee zero-fills them first (on `stream`).
+ * channels_last (NHWC memory) maps are accepted.  The warp-item fast paths (pooled tile assembled in shared memory and
+ * written by one TMA bulk store; backward: bulk load + vector reductions) need sampling_ratio == 2, PH == PW in {7, 14},
+ * sc == 1 (NHWC), C % 4 == 0, even sn / sh / sw, 8-byte aligned maps at least 4 columns wide and a 16-byte aligned
+ * out / grad_out; every other configuration runs the generic kernels (same results).
+ * rois [K,5] = (batch_idx as float, x1, y1, x2, y2) (TV:ops/_utils.py:18-25).  A roi with batch_idx < 0, batch_idx >= N of
+ * its level, or a roi_level outside [0, L) is padding: forward writes zeros for it, backward ignores it (no out-of-range
+ * access).  roi_level [K] i32 or NULL (all rois on level 0).  out / grad_out: [K, C, PH, PW] contiguous.
+ * Backward accumulates into grad levels with the same shapes/strides as the forward features; when zero_grad != 0 the
+ * callee zero-fills them first (on `stream`) — that needs DENSE levels (NCHW-contiguous or channels_last strides, so that
+ * the level is one run of N*C*H*W floats from `data`): anything else returns LCR_ERR_INVALID_ARG before touching memory.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct LcrFeatLevel {
   float* data;               /* features (forward, read-only) or grad_input (backward, accumulated) */
@@ -280,7 +288,7 @@ int lcr_mask_tail_f32(const float* logits, int K, int num_classes, int cls, int 
 
 /* Tile stitching.  Replaces calculate_mask_area_in_region (src/visualize.py:106-130)
  * inside filter_detections_by_border_mini_tiles (:174-257): for detection i, total[i] = #{mask > threshold}
- * and, for each of its rectangles r in rects[rect_offsets[i] .. rect_offsets[i+1]) (at most 16;
+ * and, for each of its rectangles r in rects[rect_offsets[i] .. rect_offsets[i+1]) (any number;
  * (x0,y0,x1,y1) half-open, mask coordinates, already clipped to the frame), in_region[r] = the number of
  * those pixels inside r.  Exact integer counts; the float64 fractions and the > mask_threshold decision stay
  * with the caller, as in the reference.  boxes [N,4] (optional): the detection boxes the masks were pasted

@@ -14,6 +14,8 @@ LCR_MAX_ANCHORS = 16
 LCR_MAX_LEVELS = 8
 LCR_MAX_TOPK = 8192
 LCR_MAX_NMS_BOXES = 32768
+# LcrStatus (include/lcr.h)
+LCR_OK, LCR_ERR_INVALID_ARG, LCR_ERR_CAPACITY, LCR_ERR_WORKSPACE, LCR_ERR_ALIGNMENT, LCR_ERR_CUDA, LCR_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6
 
 c_f32p = C.POINTER(C.c_float)
 c_i32p = C.POINTER(C.c_int)
@@ -71,6 +73,7 @@ SIGNATURES = {
     "lcr_error_string": (C.c_char_p, [C.c_int]),
     "lcr_last_cuda_error": (C.c_int, []),
     "lcr_launch_count": (C.c_uint64, []),
+    "lcr_set_tuning": (C.c_int, [C.c_char_p, C.c_char_p]),
     "lcr_anchors_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int, C.c_void_p]),
     "lcr_clip_boxes_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "lcr_filter_small_boxes_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
@@ -144,6 +147,30 @@ def check(rc: int, what: str = "") -> None:
         msg = lib.lcr_error_string(rc).decode()
         extra = f" (cudaError {lib.lcr_last_cuda_error()})" if rc == -5 else ""
         raise LcrError(f"liblcr {what}: {msg}{extra}")
+
+
+def set_tuning(key: str, value=None) -> None:
+    """Override (value=None: reset) one of the library's LCR_* tuning switches at run time; the environment itself is only
+    read once, when the library first consults a switch."""
+    check(load().lcr_set_tuning(key.encode(), None if value is None else str(value).encode()), "set_tuning")
+
+
+class tuning:
+    """Context manager: ``with tuning(LCR_ROI_FWD="staged"): ...`` sets switches and restores the previous state."""
+
+    def __init__(self, **switches):
+        self.switches = switches
+
+    def __enter__(self):
+        for k, v in self.switches.items():
+            set_tuning(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k in self.switches:
+            env = os.environ.get(k)
+            set_tuning(k, env)
+        return False
 
 
 def launch_count() -> int:

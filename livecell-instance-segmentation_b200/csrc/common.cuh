@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -41,6 +42,13 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 // Number of SMs of the current device (cached per device id).
 int sm_count();
+
+// Value of tuning switch `key` ("LCR_..."), or nullptr when unset.  The environment is read once per process; see api.cu.
+const char* tune_get(const char* key);
+inline bool tune_is(const char* key, const char* value) {
+  const char* v = tune_get(key);
+  return v && strcmp(v, value) == 0;
+}
 
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -168,10 +168,7 @@ __global__ void __launch_bounds__(256) mask_region_counts_kernel(const uint8_t* 
   __shared__ int s_cnt[kMaxRects + 1];
   __shared__ int4 s_rect[kMaxRects];
   const int i = blockIdx.x;
-  const int r0 = rect_offsets[i], nr = min(rect_offsets[i + 1] - r0, kMaxRects);
-  if (threadIdx.x <= kMaxRects) s_cnt[threadIdx.x] = 0;
-  if (threadIdx.x < nr) s_rect[threadIdx.x] = rects[r0 + threadIdx.x];
-  __syncthreads();
+  const int r0 = rect_offsets[i], nr_all = max(rect_offsets[i + 1] - r0, 0);
   int x1 = 0, y1 = 0, x2 = W, y2 = H;
   if (boxes) {  // same integer box as the paste kernel wrote into (src/custom_maskrcnn.py:279-283)
     const float4 b = __ldg(boxes + i);
@@ -182,26 +179,35 @@ __global__ void __launch_bounds__(256) mask_region_counts_kernel(const uint8_t* 
   }
   const uint8_t* mk = masks + (size_t)i * H * W;
   const int bw = max(x2 - x1, 0), bh = max(y2 - y1, 0);
-  int cnt[kMaxRects + 1];
+  // kMaxRects rectangles per pass over the box; a detection with more (the 25-tile stitcher needs at most 9) takes further
+  // passes instead of being truncated
+  for (int base = 0; base == 0 || base < nr_all; base += kMaxRects) {
+    const int nr = min(nr_all - base, kMaxRects);
+    __syncthreads();
+    if (threadIdx.x <= kMaxRects) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < nr) s_rect[threadIdx.x] = rects[r0 + base + threadIdx.x];
+    __syncthreads();
+    int cnt[kMaxRects + 1];
 #pragma unroll
-  for (int r = 0; r <= kMaxRects; ++r) cnt[r] = 0;
-  for (int p = threadIdx.x; p < bw * bh; p += blockDim.x) {
-    const int y = y1 + p / bw, x = x1 + p % bw;
-    if ((int)mk[(size_t)y * W + x] > thr) {
-      cnt[0]++;
+    for (int r = 0; r <= kMaxRects; ++r) cnt[r] = 0;
+    for (int p = threadIdx.x; p < bw * bh; p += blockDim.x) {
+      const int y = y1 + p / bw, x = x1 + p % bw;
+      if ((int)mk[(size_t)y * W + x] > thr) {
+        cnt[0]++;
 #pragma unroll
-      for (int r = 0; r < kMaxRects; ++r)
-        if (r < nr && x >= s_rect[r].x && x < s_rect[r].z && y >= s_rect[r].y && y < s_rect[r].w) cnt[r + 1]++;
+        for (int r = 0; r < kMaxRects; ++r)
+          if (r < nr && x >= s_rect[r].x && x < s_rect[r].z && y >= s_rect[r].y && y < s_rect[r].w) cnt[r + 1]++;
+      }
     }
-  }
 #pragma unroll
-  for (int r = 0; r <= kMaxRects; ++r) {
-    const int v = __reduce_add_sync(0xFFFFFFFFu, cnt[r]);
-    if (lane_id() == 0 && v) atomicAdd(&s_cnt[r], v);
+    for (int r = 0; r <= kMaxRects; ++r) {
+      const int v = __reduce_add_sync(0xFFFFFFFFu, cnt[r]);
+      if (lane_id() == 0 && v) atomicAdd(&s_cnt[r], v);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && base == 0) total[i] = s_cnt[0];
+    if (threadIdx.x < nr) in_region[r0 + base + threadIdx.x] = s_cnt[threadIdx.x + 1];
   }
-  __syncthreads();
-  if (threadIdx.x == 0) total[i] = s_cnt[0];
-  if (threadIdx.x < nr) in_region[r0 + threadIdx.x] = s_cnt[threadIdx.x + 1];
 }
 
 }  // namespace lcr

@@ -516,7 +516,7 @@ extern "C" int lcr_nms_f32(const float* boxes, const float* scores, const int* c
 
   const int row_blocks = (stride + 31) / 32;
   int span = ((long long)S * row_blocks * ((ws.nw + 31) / 32) >= 4ll * sm_count()) ? 32 : 8;
-  if (const char* v = getenv("LCR_NMS_SPAN")) {  // tuning switch for A/B runs (tools/bench_kernels.py)
+  if (const char* v = tune_get("LCR_NMS_SPAN")) {  // tuning switch for A/B runs (tools/bench_kernels.py)
     const int e = atoi(v);
     if (e == 8 || e == 16 || e == 32) span = e;
   }
@@ -525,7 +525,7 @@ extern "C" int lcr_nms_f32(const float* boxes, const float* scores, const int* c
   const float tf = float_threshold(iou_threshold);
   // segments of <= 2048 boxes: parallel (Jacobi) resolve on the full symmetric mask; longer ones: serial chunk walk
   bool parallel = stride <= 2048;
-  if (const char* v = getenv("LCR_NMS_RESOLVE")) parallel = parallel && strcmp(v, "serial") != 0;  // tuning switch (A/B, tests)
+  if (const char* v = tune_get("LCR_NMS_RESOLVE")) parallel = parallel && strcmp(v, "serial") != 0;  // tuning switch (A/B, tests)
   if (tf < 0.f) nms_mask_kernel<true><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, span, parallel ? 1 : 0, ws);
   else nms_mask_kernel<false><<<g2, 256, 0, st>>>(stride, tf, category != nullptr, span, parallel ? 1 : 0, ws);
   rc = after_launch();

@@ -477,9 +477,9 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
   LCR_REQUIRE((int64_t)H * W < (1ll << 31), LCR_ERR_CAPACITY);
   const int vpr = W / 16;
   const bool fast = (W % 16 == 0) && aligned_to(out, 16) && vpr <= 512;
-  const char* mode = getenv("LCR_PASTE");  // tuning switch for A/B runs: "rows16" selects the per-thread store kernel
+  const char* mode = tune_get("LCR_PASTE");  // tuning switch for A/B runs: "rows16" selects the per-thread store kernel
   int zb_bytes = kPasteZB;
-  if (const char* v = getenv("LCR_PASTE_ZB_KB")) zb_bytes = atoi(v) * 1024;   // tuning switch
+  if (const char* v = tune_get("LCR_PASTE_ZB_KB")) zb_bytes = atoi(v) * 1024;   // tuning switch
   if (zb_bytes < 1024 || zb_bytes > 128 * 1024 || zb_bytes % 1024) zb_bytes = kPasteZB;
   const size_t prob_bytes = round_up(sizeof(float) * (size_t)M * M, 16);
   const bool want_rows16 = mode && strcmp(mode, "rows16") == 0;
@@ -500,7 +500,7 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
     // and leaves 120 KB of shared memory per SM to a kernel running beside paste on another stream.
     int per_sm = (int)((227 * 1024) / (split_smem + 1024));
     int cap = 1;
-    if (const char* v = getenv("LCR_PASTE_CTAS")) cap = atoi(v);  // tuning switch
+    if (const char* v = tune_get("LCR_PASTE_CTAS")) cap = atoi(v);  // tuning switch
     if (cap >= 1 && cap < per_sm) per_sm = cap;
     const long long max_blocks = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
     const int blocks = (int)((long long)N < max_blocks ? N : max_blocks);
@@ -524,7 +524,7 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
     // 5, 2.25 at 1) and leave 140 KB of shared memory per SM to a kernel running beside paste on another stream.
     int per_sm = (int)((227 * 1024) / (bulk_smem + 1024));
     int cap = 2;
-    if (const char* v = getenv("LCR_PASTE_CTAS")) cap = atoi(v);  // tuning switch
+    if (const char* v = tune_get("LCR_PASTE_CTAS")) cap = atoi(v);  // tuning switch
     if (cap >= 1 && cap < per_sm) per_sm = cap;
     const long long max_blocks = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
     const int blocks = (int)((long long)N < max_blocks ? N : max_blocks);

@@ -1562,10 +1562,6 @@ static int launch_fast(const RoiParams& p, float* out_or_gout, cudaStream_t st) 
 
 // Tuning switch read per call (A/B runs): LCR_ROI_FWD = "cta" selects the per-CTA kernel,
 // LCR_ROI_STREAM_OUT = "0" drops the evict-first hint of the output stores.
-static bool env_is(const char* name, const char* value) {
-  const char* v = getenv(name);
-  return v && strcmp(v, value) == 0;
-}
 
 template <int P, int XB, int CSW>
 static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
@@ -1575,7 +1571,7 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
   const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<P>);
   const long long items = (long long)p.K * groups;
   int ipw = items >= (long long)WARPS * 2 * 4 * sm_count() ? 2 : 1;  // items per warp per CTA (small K: spread over all SMs)
-  if (const char* v = getenv("LCR_ROI_IPW")) ipw = atoi(v);
+  if (const char* v = tune_get("LCR_ROI_IPW")) ipw = atoi(v);
   long long want = (items + WARPS - 1) / WARPS;
   if (ipw > 0) {
     want = (items + (long long)WARPS * ipw - 1) / ((long long)WARPS * ipw);
@@ -1596,7 +1592,7 @@ static int launch_fwd_warp(const RoiParams& p, float* out, cudaStream_t st) {
     configured_dev = dev;
   }
   // flags: bit 0 = evict-first output stores, bit 1 = per-warp tables even when a RoI has exactly WARPS channel groups
-  const int flags = (env_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (env_is("LCR_ROI_SHARED_TABLES", "0") ? 2 : 0);
+  const int flags = (tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (tune_is("LCR_ROI_SHARED_TABLES", "0") ? 2 : 0);
   kern<<<blocks, WARPS * 32, smem, st>>>(p, out, groups, flags, ipw);
   return after_launch();
 }
@@ -1620,7 +1616,7 @@ static int launch_bwd_warp(const RoiParams& p, const float* gout, cudaStream_t s
     if (e != cudaSuccess) return cuda_status(e);
     configured_dev = dev;
   }
-  kern<<<(unsigned)want, WARPS * 32, smem, st>>>(p, gout, groups, env_is("LCR_ROI_SHARED_TABLES", "0") ? 2 : 0, ipw);
+  kern<<<(unsigned)want, WARPS * 32, smem, st>>>(p, gout, groups, tune_is("LCR_ROI_SHARED_TABLES", "0") ? 2 : 0, ipw);
   return after_launch();
 }
 
@@ -1654,7 +1650,7 @@ static int launch_fwd_staged(const RoiParams& p, float* out, cudaStream_t st, in
   using WI = WarpItem<7, XB>;
   constexpr int WARPS = 256 / WI::kChannels;
   size_t ring = kStRing;
-  if (const char* v = getenv("LCR_ROI_RING_KB")) ring = (size_t)(atoi(v) > 0 ? atoi(v) : 56) * 1024;  // > 56: one CTA per SM
+  if (const char* v = tune_get("LCR_ROI_RING_KB")) ring = (size_t)(atoi(v) > 0 ? atoi(v) : 56) * 1024;  // > 56: one CTA per SM
   const size_t fixed = sizeof(float) * 256 * 49 + kStDescs * sizeof(StagedDesc) + (2 * kStBars + 2 * kStDescs) * sizeof(uint64_t) +
                        kStBars * sizeof(uint32_t);
   if (ring + fixed > 227 * 1024) ring = (227 * 1024 - fixed) / 1024 * 1024;
@@ -1662,7 +1658,7 @@ static int launch_fwd_staged(const RoiParams& p, float* out, cudaStream_t st, in
   // RoIs per CTA: long enough to amortise the pipeline fill, short enough that small K still covers every SM twice
   int rpc = p.K / (2 * sm_count());
   rpc = rpc < 1 ? 1 : (rpc > 8 ? 8 : rpc);
-  if (const char* v = getenv("LCR_ROI_RPC")) rpc = atoi(v) > 0 ? atoi(v) : rpc;
+  if (const char* v = tune_get("LCR_ROI_RPC")) rpc = atoi(v) > 0 ? atoi(v) : rpc;
   const long long want = ((long long)p.K + rpc - 1) / rpc;
   LCR_REQUIRE(want < (1ll << 31), LCR_ERR_CAPACITY);
   auto kern = roi_fwd_staged_kernel<XB, CSW>;
@@ -1696,13 +1692,13 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
     // covered by the GPU tests, but measured SLOWER than the warp kernel on B200 (bench list 1.60 vs 1.46 ms,
     // profiles/r02_roi_staged_ab.jsonl): staging moves every window byte through the SM's 128 B/clk shared-memory data path
     // twice (copy-engine fill + LDS) where a global load passes once.  It is therefore opt-in: LCR_ROI_FWD=staged.
-    if (PH == 7 && staged_eligible(p) && (env_is("LCR_ROI_FWD", "staged") || env_is("LCR_ROI_FWD", "staged_direct"))) {
+    if (PH == 7 && staged_eligible(p) && (tune_is("LCR_ROI_FWD", "staged") || tune_is("LCR_ROI_FWD", "staged_direct"))) {
       // flags: bit 0 = evict-first output stores, bit 2 = stage nothing (every RoI gathered by the consumers: A/B)
-      const int flags = (env_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (env_is("LCR_ROI_FWD", "staged_direct") ? 4 : 0);
-      if (env_is("LCR_ROI_STAGED_WARPS", "4")) return p.C == 256 ? launch_fwd_staged<7, 256>(p, out, st, flags) : launch_fwd_staged<7, 0>(p, out, st, flags);
+      const int flags = (tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (tune_is("LCR_ROI_FWD", "staged_direct") ? 4 : 0);
+      if (tune_is("LCR_ROI_STAGED_WARPS", "4")) return p.C == 256 ? launch_fwd_staged<7, 256>(p, out, st, flags) : launch_fwd_staged<7, 0>(p, out, st, flags);
       return p.C == 256 ? launch_fwd_staged<4, 256>(p, out, st, flags) : launch_fwd_staged<4, 0>(p, out, st, flags);
     }
-    if (warp_eligible(p) && !env_is("LCR_ROI_FWD", "cta")) {
+    if (warp_eligible(p) && !tune_is("LCR_ROI_FWD", "cta")) {
       // (P = 7 with 32-channel items — half-warps taking x-bins 0-3 / 4-6, XB = 4, 6 CTAs/SM instead of 4 — was measured
       // 10 % slower than the 64-channel items on B200: the extra occupancy does not pay for the 8-slots-for-7-bins padding.)
       if (PH == 7) return all_sw_equal(p, 256) ? launch_fwd_warp<7, 7, 256>(p, out, st) : launch_fwd_warp<7, 7, 0>(p, out, st);
@@ -1726,8 +1722,15 @@ extern "C" int lcr_roi_align_bwd_f32(const float* grad_out, const LcrFeatLevel* 
   if (rc != LCR_OK) return rc;
   cudaStream_t st = as_stream(stream);
   if (zero_grad) {
+    for (int l = 0; l < L; ++l) {  // dense levels only: the level must be exactly one run of N*C*H*W floats from `data`
+      const LvParam& v = p.lv[l];
+      const long long HW = (long long)v.H * v.W;
+      const bool sn_ok = v.N == 1 || v.sn == HW * C;  // a size-1 batch dimension may carry any stride
+      const bool nchw = v.sw == 1 && v.sh == v.W && v.sc == HW && sn_ok;
+      const bool nhwc = v.sc == 1 && v.sw == C && v.sh == (long long)v.W * C && sn_ok;
+      LCR_REQUIRE(nchw || nhwc, LCR_ERR_INVALID_ARG);
+    }
     for (int l = 0; l < L; ++l) {
-      // dense levels only (NCHW or NHWC contiguous): the byte extent is N*C*H*W floats
       const LvParam& v = p.lv[l];
       cudaError_t e = cudaMemsetAsync(v.data, 0, sizeof(float) * (size_t)v.N * C * v.H * v.W, st);
       if (e != cudaSuccess) return cuda_status(e);
@@ -1736,7 +1739,7 @@ extern "C" int lcr_roi_align_bwd_f32(const float* grad_out, const LcrFeatLevel* 
   if (K == 0) return LCR_OK;
   LCR_REQUIRE(grad_out, LCR_ERR_INVALID_ARG);
   if (fast_eligible(p, grad_out)) {
-    if (warp_eligible(p) && !env_is("LCR_ROI_BWD", "cta")) {
+    if (warp_eligible(p) && !tune_is("LCR_ROI_BWD", "cta")) {
       if (PH == 7) return all_sw_equal(p, 256) ? launch_bwd_warp<7, 7, 256>(p, grad_out, st) : launch_bwd_warp<7, 7, 0>(p, grad_out, st);
       return all_sw_equal(p, 256) ? launch_bwd_warp<14, 7, 256>(p, grad_out, st) : launch_bwd_warp<14, 7, 0>(p, grad_out, st);
     }

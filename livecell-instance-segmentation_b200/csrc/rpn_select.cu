@@ -645,7 +645,7 @@ extern "C" int lcr_rpn_select_f32(const LcrRpnLevel* levels_host, int L, int B, 
     configured_smem = smem;
   }
   cudaStream_t st = as_stream(stream);
-  const char* mode = getenv("LCR_SELECT");  // tuning switch for A/B runs: "general" disables the threshold-first path
+  const char* mode = tune_get("LCR_SELECT");  // tuning switch for A/B runs: "general" disables the threshold-first path
   const bool fast = !(mode && strcmp(mode, "general") == 0);
   if (fast) {
     // logit band outside which the threshold decision needs no sigmoid: logit(thr) -+ 0.01 (thr away from 0 and 1)

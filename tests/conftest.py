@@ -40,6 +40,23 @@ def synth():
     return s
 
 
+@pytest.fixture
+def tune():
+    """Set liblcr tuning switches for one test (the library reads the environment only once, so tests go through
+    lcr_set_tuning); everything set here is reset afterwards."""
+    from livecell_instance_segmentation_b200 import _lib
+    touched = set()
+
+    def setter(**switches):
+        for k, v in switches.items():
+            touched.add(k)
+            _lib.set_tuning(k, v)
+
+    yield setter
+    for k in touched:
+        _lib.set_tuning(k, os.environ.get(k))
+
+
 def pytest_collection_modifyitems(config, items):
     """GPU tests are skipped (not failed) where no CUDA device exists."""
     try:

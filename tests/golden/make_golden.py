@@ -173,6 +173,16 @@ def gen_roi_align():
     big = synth.make_rois(4096, 42, mode="fpn")[:, 1:]
     out["lm_boxes"], out["lm_levels"] = big, LevelMapper(2, 5)([T(big)]).numpy()
     save("roi_align", **out)
+    # C = 64: a reference-run fixture that reaches the warp-item / staged fast paths (C % 64 == 0, channels_last),
+    # forward and backward; inputs are regenerated from the seeds, only torchvision's outputs are stored
+    feat = synth.make_features(1, 64, 40, 48, seed=51)
+    rois = synth.make_rois(16, 52, img_h=160, img_w=192, edge_cases=True)
+    op = RoIAlign(output_size=(7, 7), spatial_scale=0.25, sampling_ratio=2)
+    f = T(feat).clone().requires_grad_(True)
+    y = op(f, T(rois))
+    g = np.random.RandomState(53).standard_normal(tuple(y.shape)).astype(np.float32)
+    y.backward(T(g))
+    save("roi_align_c64", out=y.detach().numpy(), gin=f.grad.numpy(), seeds=np.array([51, 52, 53]), rois=rois)
 
 
 def gen_paste():
@@ -396,6 +406,9 @@ def gen_tv_paste():
 
 
 if __name__ == "__main__":
+    if "--only-roi" in sys.argv:
+        gen_roi_align()
+        sys.exit(0)
     if "--only-tv" in sys.argv:
         gen_tv_rpn()
         gen_tv_paste()

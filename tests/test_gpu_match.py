@@ -177,3 +177,26 @@ def test_mask_region_counts_with_boxes(ops, oracle, synth):
     for bx in (None, T(boxes)):
         t, r = ops.mask_region_counts(masks, T(rects.reshape(-1, 4).astype(np.int32)), T(ro.astype(np.int32)), boxes=bx)
         assert np.array_equal(N(t), t_ref) and np.array_equal(N(r), r_ref)
+
+
+def test_mask_region_counts_many_and_ragged_rect_lists(ops, oracle, synth):
+    """more than 16 rectangles per detection used to be truncated silently; ragged lists (0, 1, 16, 17, 40
+    rectangles) must all be counted."""
+    from gpu_util import N, T
+    n, H, W = 6, 222, 300
+    boxes = synth.make_det_boxes(n, 21)
+    boxes[:, [0, 2]] = boxes[:, [0, 2]].clip(0, W)
+    boxes[:, [1, 3]] = boxes[:, [1, 3]].clip(0, H)
+    masks = ops.paste_masks(T(synth.make_mask_probs(n, 28, 22)), T(boxes), H, W)
+    rng = np.random.RandomState(5)
+    per = [0, 1, 16, 17, 40, 33]
+    ro = np.concatenate([[0], np.cumsum(per)])
+    R = int(ro[-1])
+    x0, y0 = rng.randint(0, W - 20, size=R), rng.randint(0, H - 20, size=R)
+    rects = np.stack([x0, y0, np.minimum(x0 + rng.randint(1, 200, size=R), W), np.minimum(y0 + rng.randint(1, 200, size=R), H)], axis=-1)
+    rects[ro[4] + 20] = rects[ro[5] + 32] = [0, 0, W, H]             # rectangles past the 16th that certainly see pixels
+    t_ref, r_ref = oracle.mask_region_counts(N(masks), rects, ro)
+    for bx in (None, T(boxes)):
+        t, r = ops.mask_region_counts(masks, T(rects.astype(np.int32)), T(ro.astype(np.int32)), boxes=bx)
+        assert np.array_equal(N(t), t_ref) and np.array_equal(N(r), r_ref)
+    assert r_ref[ro[4] + 20] == t_ref[4] > 0 and r_ref[ro[5] + 32] == t_ref[5] > 0

@@ -164,7 +164,7 @@ def test_multilevel_fpn_rois_vs_oracle(ops, oracle, synth, P):
 
 @pytest.mark.parametrize("C,K,mode,levels", [(256, 600, "anchor", 1), (256, 37, "anchor", 1), (256, 3000, "fpn", 4), (128, 300, "fpn", 1),
                                               (64, 129, "anchor", 1), (192, 64, "fpn", 2)])
-def test_staged_forward_is_bit_identical_to_the_warp_kernel(ops, synth, oracle, monkeypatch, C, K, mode, levels):
+def test_staged_forward_is_bit_identical_to_the_warp_kernel(ops, synth, oracle, tune, C, K, mode, levels):
     """roi_fwd_staged_kernel (window rows staged through shared memory by bulk copies, producer warp + pooling warps)
     performs the arithmetic of roi_fwd_warp_kernel operation for operation: same bits, for staged RoIs, for the wide RoIs
     its consumers gather themselves, for padding rows and for every edge case; and both stay within 1e-5 of the oracle."""
@@ -182,21 +182,19 @@ def test_staged_forward_is_bit_identical_to_the_warp_kernel(ops, synth, oracle, 
         lv = oracle.level_map(rois[:, 1:], 2, 1 + levels, 224.0, 4).astype(np.int32)
     fd = [nhwc(T(f)) for f in feats]
     lvd = None if lv is None else T(lv)
-    from livecell_instance_segmentation_b200 import _lib
-    monkeypatch.delenv("LCR_ROI_FWD", raising=False)                 # default dispatch: the warp kernel
+    tune(LCR_ROI_FWD=None)                                           # default dispatch: the warp kernel
     ref = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
-    monkeypatch.setenv("LCR_ROI_FWD", "staged")
+    tune(LCR_ROI_FWD="staged")
     got = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
     assert np.array_equal(got, ref)                                  # 8 pooling warps of 32 channels per CTA
-    monkeypatch.setenv("LCR_ROI_STAGED_WARPS", "4")                  # 4 pooling warps of 64 channels
+    tune(LCR_ROI_STAGED_WARPS="4")                                   # 4 pooling warps of 64 channels
     assert np.array_equal(N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False)), ref)
-    monkeypatch.delenv("LCR_ROI_STAGED_WARPS")
-    monkeypatch.setenv("LCR_ROI_FWD", "staged_direct")               # same kernel, nothing staged
+    tune(LCR_ROI_STAGED_WARPS=None)
+    tune(LCR_ROI_FWD="staged_direct")                                # same kernel, nothing staged
     assert np.array_equal(N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False)), ref)
-    monkeypatch.setenv("LCR_ROI_RPC", "1")
-    monkeypatch.setenv("LCR_ROI_FWD", "staged")
+    tune(LCR_ROI_RPC="1", LCR_ROI_FWD="staged")
     assert np.array_equal(N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False)), ref)
-    monkeypatch.setenv("LCR_ROI_RPC", "37")                          # long CTAs: ring wrap-around, descriptor reuse
+    tune(LCR_ROI_RPC="37")                                           # long CTAs: ring wrap-around, descriptor reuse
     assert np.array_equal(N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False)), ref)
     if K <= 600:
         live = rois[:, 0] >= 0
@@ -206,3 +204,64 @@ def test_staged_forward_is_bit_identical_to_the_warp_kernel(ops, synth, oracle, 
             want = oracle.multiscale_roi_align_fwd(feats, scales, rois[live], lv[live], 7, 7, 2, False)
         assert_close_rel(got[live], want, RTOL)
         assert not got[~live].any()
+
+
+@pytest.mark.parametrize("path", ["warp", "staged", "cta", "generic_nchw"])
+def test_c64_reference_fixture_elementwise(ops, golden, synth, oracle, tune, path):
+    """tests/golden/roi_align_c64.npz: torchvision's compiled CPU op on a 64-channel map (make_golden.py:gen_roi_align) — the
+    reference-run fixture that reaches the warp-item, staged and per-CTA fast paths (C % 64 == 0, channels_last) and the generic
+    NCHW kernel; forward AND backward, checked ELEMENTWISE against the pooled magnitude (gpu_util.assert_close_elementwise),
+    not only in max-norm."""
+    from gpu_util import N, T, nhwc, assert_close_elementwise, assert_close_rel
+    g = golden("roi_align_c64")
+    s_feat, s_rois, s_g = [int(v) for v in g["seeds"]]
+    feat = synth.make_features(1, 64, 40, 48, seed=s_feat)
+    rois = g["rois"]
+    assert np.array_equal(rois, synth.make_rois(16, s_rois, img_h=160, img_w=192, edge_cases=True))
+    gout = np.random.RandomState(s_g).standard_normal((16, 64, 7, 7)).astype(np.float32)
+    if path in ("staged", "cta"):
+        tune(LCR_ROI_FWD=path, LCR_ROI_BWD=path)
+    fd = T(feat) if path == "generic_nchw" else nhwc(T(feat))
+    out = N(ops.roi_align_fwd([fd], [0.25], T(rois), None, (7, 7), 2, False))
+    mag = oracle.roi_align_fwd(np.abs(feat), rois, 7, 7, 0.25, 2, False)
+    worst, plain = assert_close_elementwise(out, g["out"], mag, RTOL, f"forward[{path}]")
+    assert_close_rel(out, g["out"], RTOL)
+    gin = torch.full((1, 64, 40, 48), 3.0, device="cuda:0")
+    if path != "generic_nchw":
+        gin = gin.contiguous(memory_format=torch.channels_last)
+    ops.roi_align_bwd(T(gout), [gin], [0.25], T(rois), None, 2, False, zero_grad=True)
+    gmag = oracle.roi_align_bwd(np.abs(gout), rois, feat.shape, 0.25, 2, False)
+    bw, bplain = assert_close_elementwise(N(gin), g["gin"], gmag, RTOL, f"backward[{path}]")
+    print(f"[roi_align c64 {path}] forward worst err/magnitude {worst:.2e} (plain relative {plain:.2e}); backward {bw:.2e} ({bplain:.2e})")
+
+
+def test_abi_rejects_non_dense_zero_fill_and_ignores_bad_levels(ops, synth):
+    """VERDICT r01 hygiene: lcr_roi_align_bwd_f32 with zero_grad memsets N*C*H*W floats from `data`, so a level that is
+    not one dense run must be refused (LCR_ERR_INVALID_ARG) instead of zeroing its neighbours; a roi_level outside [0, L) or a
+    batch index >= N makes the RoI padding (zero rows forward, ignored backward) instead of an out-of-range access."""
+    import ctypes as C
+    from gpu_util import N, T, nhwc
+    from livecell_instance_segmentation_b200 import _lib
+    lib = _lib.load()
+    big = torch.full((1, 8, 12, 32), 5.0, device="cuda:0")
+    view = big[:, :, :, ::2]                                         # every other column: not dense
+    rois = T(synth.make_rois(6, 3, img_h=48, img_w=64))
+    gout = torch.ones((6, 8, 7, 7), device="cuda:0")
+    rc = lib.lcr_roi_align_bwd_f32(gout.data_ptr(), ops._feat_levels([view], [0.25]), 1, 8, rois.data_ptr(), None, 6, 7, 7, 2, 0, 1,
+                                   torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rc == _lib.LCR_ERR_INVALID_ARG and bool((big == 5.0).all())
+    feat = nhwc(T(synth.make_features(2, 64, 12, 16, seed=4)))
+    r = synth.make_rois(8, 5, img_h=48, img_w=64, batch=2)
+    lv = np.zeros(8, np.int32)
+    lv[1], lv[2] = 7, -3                                             # levels that do not exist
+    r[3, 0] = 2.0                                                    # batch index past the end
+    out = N(ops.roi_align_fwd([feat], [0.25], T(r), T(lv), (7, 7), 2, False))
+    assert not out[[1, 2, 3]].any() and out[[0, 4, 5, 6, 7]].any(axis=(1, 2, 3)).all()
+    gin = torch.zeros_like(feat)
+    ops.roi_align_bwd(T(np.ones_like(out)), [gin], [0.25], T(r), T(lv), 2, False, zero_grad=True)
+    good = np.ones(8, bool)
+    good[[1, 2, 3]] = False
+    gref = torch.zeros_like(feat)
+    ops.roi_align_bwd(T(np.ones_like(out[good])), [gref], [0.25], T(r[good]), T(lv[good]), 2, False, zero_grad=True)
+    assert torch.allclose(gin, gref, rtol=0, atol=1e-5)

@@ -195,11 +195,9 @@ def test_threshold_first_path_boundaries(ops, oracle):
         kw = dict(k=300, img_size=(80, 96), score_thresh=0.3, min_size=0.0, strides=[4], base=torch.from_numpy(base),
                   score_strict=strict)
         fast = run_select(ops, obj, **kw)
-        os.environ["LCR_SELECT"] = "general"
-        try:
+        from livecell_instance_segmentation_b200 import _lib
+        with _lib.tuning(LCR_SELECT="general"):
             general = run_select(ops, obj, **kw)
-        finally:
-            os.environ.pop("LCR_SELECT", None)
         n = int(fast[3][0, 0])
         assert n == int(general[3][0, 0]) and 150 < n < 250
         for a, b in zip(fast[:3], general[:3]):

@@ -282,3 +282,16 @@ def test_torchvision_paste_masks(oracle, golden):
         want = g[f"{tag}_out"]
         assert np.array_equal(out != 0, want != 0)                   # the same pixels are written
         np.testing.assert_allclose(out, want, rtol=0, atol=1e-6)     # ATen's CPU bilinear is FMA-contracted per build
+
+
+def test_roi_align_c64_reference_fixture(oracle, golden, synth):
+    """The 64-channel reference-run fixture (fast-path shape): the oracle reproduces torchvision's compiled CPU op bit for bit,
+    forward and backward."""
+    g = golden("roi_align_c64")
+    s_feat, s_rois, s_g = [int(v) for v in g["seeds"]]
+    feat = synth.make_features(1, 64, 40, 48, seed=s_feat)
+    assert np.array_equal(g["rois"], synth.make_rois(16, s_rois, img_h=160, img_w=192, edge_cases=True))
+    assert np.array_equal(oracle.roi_align_fwd(feat, g["rois"], 7, 7, 0.25, 2, False), g["out"])
+    gout = np.random.RandomState(s_g).standard_normal((16, 64, 7, 7)).astype(np.float32)
+    gin = oracle.roi_align_bwd(gout, g["rois"], feat.shape, 0.25, 2, False)
+    np.testing.assert_allclose(gin, g["gin"], rtol=0, atol=1e-5 * np.abs(g["gin"]).max())

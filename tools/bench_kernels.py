@@ -46,7 +46,7 @@ def main():
     args = ap.parse_args()
     only = set(args.only.split(","))
     import torch
-    from livecell_instance_segmentation_b200 import ops
+    from livecell_instance_segmentation_b200 import _lib, ops
     from livecell_instance_segmentation_b200.pipeline import RegionConfig, RegionPipeline
 
     dev = torch.device("cuda:0")
@@ -70,8 +70,9 @@ def main():
     def setenv(env):
         for k in ("LCR_ROI_RING_KB", "LCR_ROI_STAGED_WARPS", "LCR_ROI_RPC", "LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_PASTE_CTAS", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
                   "LCR_NMS_RESOLVE"):
-            os.environ.pop(k, None)
-        os.environ.update(env)
+            _lib.set_tuning(k, None)       # the library reads the environment only once: switches go through lcr_set_tuning
+        for k, v in env.items():
+            _lib.set_tuning(k, v)
 
     if "roi" in only:
         bytes_roi = 4 * n_props * B.C * 49 + F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS

@@ -59,7 +59,8 @@ def _worker(rank, world, port, n_frames, q):
     rec2, cnt2 = hnd.wait()
     torch.cuda.synchronize(dev)
     assert torch.equal(rec, rec2) and torch.equal(cnt, cnt2)
-    q.put((rank, rec.cpu().numpy(), cnt.cpu().numpy(), int(sp.masks.sum().item())))
+    valid = (torch.arange(40, device=dev)[None, :] < sp.counts[:, None]).reshape(-1)       # padded slots are never written
+    q.put((rank, rec.cpu().numpy(), cnt.cpu().numpy(), int(sp.masks[valid].sum().item())))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -187,7 +187,10 @@ def test_mask_region_counts_many_and_ragged_rect_lists(ops, oracle, synth):
     boxes = synth.make_det_boxes(n, 21)
     boxes[:, [0, 2]] = boxes[:, [0, 2]].clip(0, W)
     boxes[:, [1, 3]] = boxes[:, [1, 3]].clip(0, H)
-    masks = ops.paste_masks(T(synth.make_mask_probs(n, 28, 22)), T(boxes), H, W)
+    boxes[4], boxes[5] = [40.0, 30.0, 120.0, 90.0], [100.5, 60.2, 180.0, 170.9]      # certainly inside the frame
+    probs = synth.make_mask_probs(n, 28, 22)
+    probs[4:] = 0.9                                                   # fully-on masks
+    masks = ops.paste_masks(T(probs), T(boxes), H, W)
     rng = np.random.RandomState(5)
     per = [0, 1, 16, 17, 40, 33]
     ro = np.concatenate([[0], np.cumsum(per)])

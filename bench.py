@@ -313,7 +313,7 @@ def run_ours(args):
     host["feat"].copy_(feat_d.permute(0, 2, 3, 1))
 
     # ---- the product path: StreamedRegionPipeline over static input buffers -----------------------------------------
-    sp = StreamedRegionPipeline(cfg, F, (C, FH, FW), (IMG_H, IMG_W), num_anchors=A, chunks=args.chunks, device=dev)
+    sp = StreamedRegionPipeline(cfg, F, (C, FH, FW), (IMG_H, IMG_W), num_anchors=A, chunks=args.chunks, device=dev, depth=args.depth)
     sp.inputs["obj"].copy_(host["obj"])
     sp.inputs["bs"].copy_(host["bs"])
     sp.inputs["probs"].copy_(host["probs"])
@@ -329,7 +329,8 @@ def run_ours(args):
     if not args.no_graph:
         try:
             sp.capture()
-            launch_mode = f"cuda_graph_replay ({2 * sp.chunks} graphs per step: select/NMS/RoIAlign and paste of each of {sp.chunks} sub-batches)"
+            launch_mode = (f"cuda_graph_replay ({2 * sp.chunks} graphs per step: select/NMS/RoIAlign and paste of each of {sp.chunks} sub-batches, "
+                           f"{sp.depth} alternating buffer sets)")
         except Exception as exc:          # capture unsupported for some reason: time the eager launches instead
             print(f"bench: CUDA graph capture failed ({exc!r}); timing eager launches", file=sys.stderr)
             sp._graphs = None
@@ -649,7 +650,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
-    ap.add_argument("--chunks", type=int, default=4, help="sub-batches per step of the streamed pipeline (paste overlaps the next one)")
+    ap.add_argument("--chunks", type=int, default=2, help="sub-batches per step of the streamed pipeline (paste overlaps the next one)")
+    ap.add_argument("--depth", type=int, default=2, help="buffer sets of the streamed pipeline (2: a step's first stages run under the previous step's last paste)")
     ap.add_argument("--chunk-frames", type=int, default=8, help="e2e: frames per H2D/compute pipeline chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-python", action="store_true", help="skip the unmodified-reference CPU leg (baseline/_ref)")

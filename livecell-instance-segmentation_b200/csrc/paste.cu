@@ -268,17 +268,18 @@ __global__ void __launch_bounds__(kPasteThreads) paste_bulk_kernel(const float* 
 // against its all-empty-boxes floor.
 constexpr int kSplitThreads = 160;
 constexpr int kComposers = 128;
-constexpr int kSlots = 8;
+constexpr int kSlots = 8;   // default ring depth; 4 / 2 leave more shared memory to a kernel co-running on another stream
 
 __device__ __forceinline__ void composer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kComposers) : "memory"); }
 
+template <int SLOTS>
 __global__ void __launch_bounds__(kSplitThreads) paste_split_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
                                                                     const uint8_t* __restrict__ valid, int N, int M, int H, int W,
                                                                     float thr, uint32_t on_value, uint8_t* __restrict__ out, int zb_bytes) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint8_t* zb = smem;
-  uint8_t* rb = smem + zb_bytes;                                                   // kSlots chunks of kPasteRB bytes
-  float* sprob = reinterpret_cast<float*>(smem + zb_bytes + kSlots * kPasteRB);   // [M*M]
+  uint8_t* rb = smem + zb_bytes;                                                   // SLOTS chunks of kPasteRB bytes
+  float* sprob = reinterpret_cast<float*>(smem + zb_bytes + SLOTS * kPasteRB);   // [M*M]
   const int tid = threadIdx.x;
   for (int i = tid; i < zb_bytes / 16; i += kSplitThreads) reinterpret_cast<uint4*>(zb)[i] = make_uint4(0u, 0u, 0u, 0u);
   paste_fence_async();
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(kSplitThreads) paste_split_kernel(const float*
       const int rows = min(chunk_rows, pb.y2 - yc);
       uint8_t* chunk = rb + slot * kPasteRB;
       // the slot's previous store (kSlots groups ago) must have finished reading it: at most kSlots - 1 younger groups pending
-      if (ct == 0) paste_bulk_wait_read<kSlots - 1>();
+      if (ct == 0) paste_bulk_wait_read<SLOTS - 1>();
       composer_barrier();  // (also publishes sprob)
       for (int i = ct; i < rows * vpr; i += kComposers) {
         const int r = i / vpr, xv = i - r * vpr;
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(kSplitThreads) paste_split_kernel(const float*
         paste_bulk_store(frame + (size_t)yc * W, chunk, (uint32_t)(rows * W), pol);
         paste_bulk_commit();
       }
-      slot = slot + 1 == kSlots ? 0 : slot + 1;
+      slot = slot + 1 == SLOTS ? 0 : slot + 1;
     }
   }
   if (ct == 0) paste_bulk_wait_read<0>();
@@ -484,17 +485,23 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
   const size_t prob_bytes = round_up(sizeof(float) * (size_t)M * M, 16);
   const bool want_rows16 = mode && strcmp(mode, "rows16") == 0;
   const bool want_single = mode && (strcmp(mode, "single") == 0 || strcmp(mode, "zeros_last") == 0);  // the r01d single-role kernel
-  const size_t split_smem = (size_t)zb_bytes + (size_t)kSlots * kPasteRB + prob_bytes;
+  int slots = kSlots;
+  if (const char* v = tune_get("LCR_PASTE_SLOTS")) slots = atoi(v);  // tuning switch: 8 (default), 4 or 2 ring slots
+  if (slots != 8 && slots != 4 && slots != 2) slots = kSlots;
+  const size_t split_smem = (size_t)zb_bytes + (size_t)slots * kPasteRB + prob_bytes;
   if (fast && W <= kPasteRB && split_smem <= 200 * 1024 && !want_rows16 && !want_single) {
+    auto kern = slots == 8 ? paste_split_kernel<8> : (slots == 4 ? paste_split_kernel<4> : paste_split_kernel<2>);
     static thread_local int configured_dev = -1;
-    static thread_local size_t configured_smem = 0;
+    static thread_local size_t configured_smem[3] = {0, 0, 0};
+    const int ki = slots == 8 ? 0 : (slots == 4 ? 1 : 2);
     int dev = 0;
     cudaGetDevice(&dev);
-    if (configured_dev != dev || configured_smem < split_smem) {
-      cudaError_t e = cudaFuncSetAttribute(paste_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem);
+    if (configured_dev != dev || configured_smem[ki] < split_smem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem);
       if (e != cudaSuccess) return cuda_status(e);
+      if (configured_dev != dev) configured_smem[0] = configured_smem[1] = configured_smem[2] = 0;
       configured_dev = dev;
-      configured_smem = split_smem;
+      configured_smem[ki] = split_smem;
     }
     // One persistent CTA per SM is enough for the zero issuer to keep the copy engine saturated (1.945 ms; 2 per SM: 1.959)
     // and leaves 120 KB of shared memory per SM to a kernel running beside paste on another stream.
@@ -504,8 +511,8 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
     if (cap >= 1 && cap < per_sm) per_sm = cap;
     const long long max_blocks = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
     const int blocks = (int)((long long)N < max_blocks ? N : max_blocks);
-    paste_split_kernel<<<blocks, kSplitThreads, split_smem, as_stream(stream)>>>(probs, boxes, valid, N, M, H, W, threshold,
-                                                                                (uint32_t)on_value, out, zb_bytes);
+    kern<<<blocks, kSplitThreads, split_smem, as_stream(stream)>>>(probs, boxes, valid, N, M, H, W, threshold, (uint32_t)on_value, out,
+                                                                  zb_bytes);
     return after_launch();
   }
   const size_t bulk_smem = (size_t)zb_bytes + 2 * kPasteRB + prob_bytes;

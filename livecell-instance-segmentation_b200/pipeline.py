@@ -166,11 +166,14 @@ class StreamedRegionPipeline:
     reference allocates them per image (src/custom_maskrcnn.py:164-207).  ``capture()`` records every sub-batch's two stage
     groups as CUDA graphs over static input buffers (`self.inputs`), after which ``run()`` only replays."""
 
-    def __init__(self, cfg: RegionConfig, frames: int, feat_shape, image_size, num_anchors: int = 9, chunks: int = 4, device=None):
+    def __init__(self, cfg: RegionConfig, frames: int, feat_shape, image_size, num_anchors: int = 9, chunks: int = 2, device=None,
+                 depth: int = 2):
         self.pipe = RegionPipeline(cfg)
         self.cfg = cfg
         self.F = int(frames)
         self.chunks = max(1, min(int(chunks), self.F))
+        self.depth = max(1, int(depth))   # sets of per-sub-batch intermediates: with 2, the front stages of a sub-batch only wait
+        # for its paste of TWO batches ago, so a batch's first stages also run under the previous batch's last paste
         self.H, self.W = int(image_size[0]), int(image_size[1])
         C, fh, fw = feat_shape
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -191,27 +194,31 @@ class StreamedRegionPipeline:
         self.proposal_counts = torch.zeros((F,), dtype=torch.int32, device=dev)
         self.side = torch.cuda.Stream(device=dev)
         self.bounds = [(c * F // self.chunks, (c + 1) * F // self.chunks) for c in range(self.chunks)]
-        self.ev_main = [torch.cuda.Event() for _ in range(self.chunks)]     # stages 1-3 of sub-batch c enqueued
-        self.ev_side = [torch.cuda.Event() for _ in range(self.chunks)]     # stage 4 of sub-batch c enqueued
-        self.used = [False] * self.chunks
+        n_slots = self.depth * self.chunks
+        self.ev_main = [torch.cuda.Event() for _ in range(n_slots)]     # stages 1-3 of (set, sub-batch) enqueued
+        self.ev_side = [torch.cuda.Event() for _ in range(n_slots)]     # stage 4 of (set, sub-batch) enqueued
+        self.used = [False] * n_slots
         self.done = torch.cuda.Event()
-        self._state = [None] * self.chunks
+        self._state = [None] * n_slots
         self._graphs = None
+        self._batch = 0
 
     # the two stage groups of one sub-batch ----------------------------------------------------------------------------
-    def _front(self, c, inp):
+    def _front(self, c, inp, slot=None):
+        slot = c if slot is None else slot
         f0, f1 = self.bounds[c]
         P = self.cfg.post_nms_top_n
         props = self.pipe.proposals(inp["obj"][f0:f1], (self.H, self.W))
         self.pipe.pool(inp["feat"][f0:f1], props.rois, out=self.roi_features[f0 * P: f1 * P])
         det = self.pipe.detections(props, inp["bs"][f0:f1])
         self.proposal_counts[f0:f1].copy_(props.counts, non_blocking=True)
-        self._state[c] = det
+        self._state[slot] = det
 
-    def _back(self, c, inp):
+    def _back(self, c, inp, slot=None):
+        slot = c if slot is None else slot
         f0, f1 = self.bounds[c]
         D = self.cfg.det_capacity
-        det = self.pipe.paste(self._state[c], inp["probs"][f0 * D: f1 * D], (self.H, self.W), out=self.masks[f0 * D: f1 * D])
+        det = self.pipe.paste(self._state[slot], inp["probs"][f0 * D: f1 * D], (self.H, self.W), out=self.masks[f0 * D: f1 * D])
         self.records[f0:f1].copy_(det.records, non_blocking=True)
         self.counts[f0:f1].copy_(det.counts, non_blocking=True)
 
@@ -227,12 +234,13 @@ class StreamedRegionPipeline:
         main.wait_stream(warm)
         torch.cuda.synchronize(self.device)
         graphs = []
-        for c in range(self.chunks):
+        for slot in range(self.depth * self.chunks):      # one pair of graphs per (set, sub-batch): own intermediates
+            c = slot % self.chunks
             gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(gf):
-                self._front(c, self.inputs)
+                self._front(c, self.inputs, slot)
             with torch.cuda.graph(gb, pool=gf.pool()):
-                self._back(c, self.inputs)
+                self._back(c, self.inputs, slot)
             graphs.append((gf, gb))
         self._graphs = graphs
         return self
@@ -245,22 +253,25 @@ class StreamedRegionPipeline:
             raise ValueError("after capture() the batch must be written into self.inputs")
         inp = self.inputs if inputs is None else inputs
         main = torch.cuda.current_stream(self.device)
+        base = (self._batch % self.depth) * self.chunks
+        self._batch += 1
         for c in range(self.chunks):
-            if self.used[c]:
-                main.wait_event(self.ev_side[c])          # the previous batch's paste of this sub-batch has read its inputs
+            slot = base + c
+            if self.used[slot]:
+                main.wait_event(self.ev_side[slot])       # this set's previous paste (`depth` batches ago) has read its inputs
             if self._graphs is not None:
-                self._graphs[c][0].replay()
+                self._graphs[slot][0].replay()
             else:
-                self._front(c, inp)
-            self.ev_main[c].record(main)
+                self._front(c, inp, slot)
+            self.ev_main[slot].record(main)
             with torch.cuda.stream(self.side):
-                self.side.wait_event(self.ev_main[c])
+                self.side.wait_event(self.ev_main[slot])
                 if self._graphs is not None:
-                    self._graphs[c][1].replay()
+                    self._graphs[slot][1].replay()
                 else:
-                    self._back(c, inp)
-                self.ev_side[c].record(self.side)
-            self.used[c] = True
+                    self._back(c, inp, slot)
+                self.ev_side[slot].record(self.side)
+            self.used[slot] = True
         self.done.record(self.side)
         if finish:
             self.finish()

@@ -160,6 +160,17 @@ def main():
         del ref
         del gout, gin
 
+    if "bwd1" in only:   # ncu target: the default backward on the bench list and on BASELINE C5 (16384 RoIs on ONE 130x176 map)
+        from livecell_instance_segmentation_b200 import synth
+        gout = torch.randn((F * B.POST_NMS, B.C, 7, 7), generator=g, device=dev)
+        gin = torch.empty((F, B.C, B.FH, B.FW), device=dev).contiguous(memory_format=torch.channels_last)
+        med, mn = timed(lambda: ops.roi_align_bwd(gout, [gin], [0.25], props.rois, None, 2, False, zero_grad=False), args.reps, flush)
+        emit(kernel="roi_align_bwd (no zero fill)", variant="bench list", ms=med, rois=n_props)
+        rois5 = torch.from_numpy(synth.make_rois(16384, 100 + 16384, mode="anchor")).to(dev)
+        med, mn = timed(lambda: ops.roi_align_bwd(gout[:16384], [gin[:1]], [0.25], rois5, None, 2, False, zero_grad=False), args.reps, flush)
+        emit(kernel="roi_align_bwd (no zero fill)", variant="C5: 16384 RoIs, one map", ms=med, rois=16384)
+        del gout, gin
+
     if "paste" in only:
         masks = torch.empty((F * B.MAX_DET, B.IMG_H, B.IMG_W), dtype=torch.uint8, device=dev)
         boxes_flat = det.boxes.reshape(-1, 4)

@@ -85,8 +85,13 @@ class RegionPipeline:
 
     # -- stage 2: RoIAlign ---------------------------------------------------------------------------
     def pool(self, features: torch.Tensor, rois: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """features: logical [B, C, h, w]; channels_last memory takes the fast path directly."""
+        """features: logical [B, C, h, w]; channels_last memory takes the fast path directly.  An NCHW map is transposed once
+        (tiled 16-byte transpose) when the pooled output outweighs it, otherwise pooled through its strides by the generic kernel."""
         c = self.cfg
+        B, C, h, w = features.shape
+        nhwc = features.stride() == (h * w * C, 1, w * C, C)
+        if not nhwc and C % 4 == 0 and rois.shape[0] * c.pooled_size * c.pooled_size >= B * h * w:
+            features = ops.to_nhwc(features)
         return ops.roi_align_fwd([features], [c.spatial_scale], rois, None, (c.pooled_size, c.pooled_size), c.sampling_ratio, False,
                                  out=out)
 

@@ -120,7 +120,7 @@ def perturb_roi_align_by_one_ulp(model, seed=99):
 def _install(patched):
     if patched:
         from livecell_instance_segmentation_b200 import install as inst
-        done = inst.install()
+        done = inst.install(batched_inference=(patched == "batched"))
         assert done, "install() patched nothing"
         return inst
     return None

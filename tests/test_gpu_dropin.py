@@ -36,7 +36,7 @@ def _launches():
     return _lib.launch_count()
 
 
-def _pair_inference(H, W, B, channels_last, n_cells):
+def _pair_inference(H, W, B, channels_last, n_cells, patched=True):
     """(untouched, patched) predictions on a tie-free seed."""
     for seed in range(6):
         ref, info = dc.run_inference(DEV, False, H, W, B, seed=seed, channels_last=channels_last, n_cells=n_cells)
@@ -46,7 +46,7 @@ def _pair_inference(H, W, B, channels_last, n_cells):
         pytest.fail("no tie-free seed found")
     assert info["roi_align_type"].startswith("torchvision")
     l0 = _launches()
-    got, ginfo = dc.run_inference(DEV, True, H, W, B, seed=seed, channels_last=channels_last, n_cells=n_cells, state=info["state"])
+    got, ginfo = dc.run_inference(DEV, patched, H, W, B, seed=seed, channels_last=channels_last, n_cells=n_cells, state=info["state"])
     assert ginfo["roi_align_type"].startswith(OURS), ginfo["roi_align_type"]
     assert _launches() > l0, "the patched model launched no liblcr kernel"
     return ref, got
@@ -66,6 +66,18 @@ def test_forward_inference_matches_the_untouched_model(shape, channels_last):
     # is pinned separately (test_generate_masks_on_identical_features, tests/test_gpu_paste.py).
     total = sum(p["masks"].size for p in ref)
     assert flips <= max(2, int(2e-7 * total)), f"{flips} of {total} mask pixels differ"
+
+
+def test_batched_forward_inference_matches_the_untouched_model():
+    """install(batched_inference=True): forward_inference without the per-image loop (the batched region pipeline around the
+    model's own heads) returns what the untouched model's loop returns (3 frames)."""
+    ref, got = _pair_inference(520, 704, 3, False, 150, patched="batched")
+    n_det = sum(len(p["boxes"]) for p in ref)
+    assert n_det > 0
+    flips = dc.compare_predictions(ref, got, score_atol=1e-6, what="batched")
+    total = sum(p["masks"].size for p in ref)
+    print(f"[dropin] batched forward_inference, 3 x 704x520: {n_det} detections, mask pixel flips {flips}")
+    assert flips <= max(2, int(2e-7 * total))
 
 
 def test_generate_masks_on_identical_features():

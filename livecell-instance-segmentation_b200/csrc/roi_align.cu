@@ -739,6 +739,222 @@ __global__ void __launch_bounds__(WARPS * 32, P == 7 ? (XB == 7 ? 4 : 6) : 2)
   if (lane == 0) bulk_wait_read_all();
 }
 
+// ---- forward, row-major warp items (P = 7) -----------------------------------------------------------
+// roi_fwd_warp_kernel walks the 14 y-samples of a RoI and keeps a two-row cache: every sample costs reuse bookkeeping
+// (SAME / SHIFT / NEW votes, register-set flips, border copies: 2 600 instructions per item for ~1 000 of payload), and
+// every distinct window row costs one exposed L2 round trip (its loads are issued, waited for and consumed before the next
+// row's are issued).  Here the RoI's y taps are turned, once per RoI, into a ROW PROGRAM: the distinct window rows in
+// ascending order, each with the (pre-added) weights it contributes to at most three consecutive bin rows.  A warp then
+//   * pools ROWS (1 or 2) window rows per phase — with 2, both rows' loads are in flight together, halving the exposed
+//     round trips per item at the cost of 42 more registers (12 instead of 16 warps per SM);
+//   * adds each x-pooled row into three accumulator sets acc0..acc2 = bin rows base, base+1, base+2 with its three weights
+//     (21 FFMA2, no mode logic); when a row's first bin row is past `base`, the finished bin rows are written to the tile and
+//     the sets rotate.
+// Rows whose weights span more than three bin rows (bins under ~0.7 feature px: RoIs under ~20 image px), windows taller
+// than 32 rows or wider than NB = 4 columns per bin take roi_warp_body as before.  Pre-adding the taps of a shared row
+// changes the rounding of the y sum by an ulp: results agree with roi_fwd_warp_kernel to ~1e-7 relative, not bit for bit.
+struct __align__(16) RowOp {
+  uint32_t off_pa;   // byte offset of the row inside the map, first bin row in the low 3 bits (rows are >= 16 bytes apart)
+  float w0, w1, w2;  // weights (count 1/4 folded in) for bin rows pa, pa + 1, pa + 2
+};
+
+// Builds the row program of the warp's current RoI into tb.xs (free once the bins are folded: run <= 4) and returns the number
+// of rows (0: every sample is outside the map -> an all-zero tile), or -1 when the RoI does not qualify.  All lanes call.
+__device__ __forceinline__ int build_row_program(WarpTables<7>& tb, uint32_t shb, int lane) {
+  constexpr uint32_t kAll = 0xffffffffu;
+  const int ylo = lane < 14 ? tb.lo[1][lane] : -1, yhi = lane < 14 ? tb.hi[1][lane] : -1;
+  const int rmin = __reduce_min_sync(kAll, ylo >= 0 ? ylo : 0x7fffffff);
+  const int rmax = __reduce_max_sync(kAll, ylo >= 0 ? yhi : -1);
+  if (rmax < 0) return 0;
+  if (rmax - rmin >= 32) return -1;
+  const int r = rmin + lane;
+  float w[7];
+#pragma unroll
+  for (int ph = 0; ph < 7; ++ph) w[ph] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 14; ++t) {
+    const int lo = tb.lo[1][t], hi = tb.hi[1][t];
+    if (lo >= 0) {
+      const AxisTapB s = tb.ys[t];
+      if (lo == r) w[t >> 1] += s.w_lo * 0.25f;
+      if (hi == r) w[t >> 1] += s.w_hi * 0.25f;
+    }
+  }
+  int pa = 7, pb = -1;
+#pragma unroll
+  for (int ph = 0; ph < 7; ++ph)
+    if (w[ph] != 0.f) {
+      pa = min(pa, ph);
+      pb = ph;
+    }
+  const bool used = pb >= 0 && r <= rmax;
+  if (!__all_sync(kAll, !used || pb - pa <= 2)) return -1;
+  const uint32_t mask = __ballot_sync(kAll, used);
+  // first bin rows must not decrease along the rows (they cannot for x2 >= x1 geometry; checked, not assumed)
+  const uint32_t before = mask & ((1u << lane) - 1u);
+  const int prev_pa = __shfl_sync(kAll, pa, before ? 31 - __clz(before) : lane);
+  if (!__all_sync(kAll, !used || !before || prev_pa <= pa)) return -1;
+  if (used) {
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+#pragma unroll
+    for (int ph = 0; ph < 7; ++ph) {
+      w0 = ph == pa ? w[ph] : w0;
+      w1 = ph == pa + 1 ? w[ph] : w1;
+      w2 = ph == pa + 2 ? w[ph] : w2;
+    }
+    RowOp op;
+    op.off_pa = ((uint32_t)r * shb) | (uint32_t)pa;
+    op.w0 = w0;
+    op.w1 = w1;
+    op.w2 = w2;
+    reinterpret_cast<RowOp*>(tb.xs)[__popc(before)] = op;
+  }
+  __syncwarp();
+  return __popc(mask);
+}
+
+template <int NB, int ROWS, int CSW>
+__device__ __forceinline__ void roi_warp_body_rm(const WarpTables<7>& tb, int nrows, const char* __restrict__ fb, uint32_t swb,
+                                                 float* __restrict__ my) {
+  constexpr int P = 7, PP = 49;
+  const uint32_t cs = CSW ? (uint32_t)CSW * 4u : swb;
+  const RowOp* rows = reinterpret_cast<const RowOp*>(tb.xs);
+  uint32_t xo[P];
+  float2 acc0[P], acc1[P], acc2[P];
+#pragma unroll
+  for (int pw = 0; pw < P; ++pw) {
+    xo[pw] = tb.xoff[pw];
+    acc0[pw] = acc1[pw] = acc2[pw] = make_float2(0.f, 0.f);
+  }
+  // (the folded x weights are re-read from shared memory per bin, one broadcast LDS.128 each: holding all 21-28 of them in
+  // registers next to two rows of loaded columns does not fit the 168 registers that 12 warps per SM allow — the spill
+  // stores of just-loaded columns serialised the two rows' loads again)
+  const bool lower = (threadIdx.x & 16) == 0;  // conflict-free tile stores, see roi_warp_body
+  float* const o_a = my + (lower ? 0 : PP);
+  float* const o_b = my + (lower ? PP : 0);
+  int base = 0;
+  auto retire = [&](int upto) {  // bin rows base .. upto-1 are complete: write them out and rotate the accumulator sets
+    while (base < upto) {
+      const int o = base * P;
+#pragma unroll
+      for (int pw = 0; pw < P; ++pw) {
+        const float e = acc0[pw].x, f = acc0[pw].y;
+        o_a[o + pw] = lower ? e : f;
+        o_b[o + pw] = lower ? f : e;
+        acc0[pw] = acc1[pw];
+        acc1[pw] = acc2[pw];
+        acc2[pw] = make_float2(0.f, 0.f);
+      }
+      ++base;
+    }
+  };
+  auto load_row = [&](const RowOp& op, float2 (&v)[P][NB]) {
+    const char* row = fb + (op.off_pa & ~7u);
+#pragma unroll
+    for (int pw = 0; pw < P; ++pw) {
+      const char* q = row + xo[pw];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) v[pw][j] = ldg_f2b(q + j * cs);
+    }
+  };
+  auto apply_row = [&](const RowOp& op, const float2 (&v)[P][NB]) {
+    retire((int)(op.off_pa & 7u));
+    const float2 w0 = splat(op.w0), w1 = splat(op.w1), w2 = splat(op.w2);
+#pragma unroll
+    for (int pw = 0; pw < P; ++pw) {
+      const float4 xw4 = tb.xw[pw];
+      const float xw[4] = {xw4.x, xw4.y, xw4.z, xw4.w};
+      float2 t = __fmul2_rn(splat(xw[0]), v[pw][0]);
+#pragma unroll
+      for (int j = 1; j < NB; ++j) t = ffma2(splat(xw[j]), v[pw][j], t);
+      acc0[pw] = ffma2(w0, t, acc0[pw]);
+      acc1[pw] = ffma2(w1, t, acc1[pw]);
+      acc2[pw] = ffma2(w2, t, acc2[pw]);
+    }
+  };
+#pragma unroll 1
+  for (int i = 0; i < nrows; i += ROWS) {
+    const RowOp ra = rows[i];
+    float2 va[P][NB];
+    load_row(ra, va);
+    if (ROWS == 2 && i + 1 < nrows) {  // warp-uniform: both rows' loads are in flight before either is consumed
+      const RowOp rb = rows[i + 1];
+      float2 vb[P][NB];
+      load_row(rb, vb);
+      apply_row(ra, va);
+      apply_row(rb, vb);
+    } else {
+      apply_row(ra, va);
+    }
+  }
+  retire(P);
+}
+
+template <int ROWS, int CSW>
+__global__ void __launch_bounds__(128, ROWS == 2 ? 3 : 4)
+    roi_fwd_rm_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out, int flags, int ipw) {
+  using WI = WarpItem<7, 7>;
+  constexpr int WARPS = 4, PP = 49;
+  constexpr uint32_t kAll = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = __shfl_sync(kAll, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * WI::kTileFloats;
+  WarpTables<7>* tbs = reinterpret_cast<WarpTables<7>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats);
+  __shared__ int s_run[WARPS], s_b[WARPS], s_lvl[WARPS], s_rows[WARPS];
+  float* my = tile + (size_t)(2 * lane) * PP;
+  const uint64_t pol = l2_policy_evict_first();
+  // C == 256: the CTA's ipw RoIs are shared by its four warps (warp = 64-channel group); warp i builds RoI i's tables
+  const int k0 = blockIdx.x * ipw;
+  if (warp < ipw && k0 + warp < p.K) {
+    const RoiGeom g = roi_geom(p, k0 + warp);
+    const bool live = __any_sync(kAll, g.live);
+    int run = -1, nrows = -1;
+    if (live) {
+      const LvParam& lv = p.lv[g.lvl];
+      run = build_tables_warp<7>(tbs[warp], g, lv, lane, 7);
+      if (run <= 4) nrows = build_row_program(tbs[warp], (uint32_t)lv.sh * 4u, lane);
+    }
+    if (lane == 0) {
+      s_run[warp] = run;
+      s_b[warp] = g.b;
+      s_lvl[warp] = live ? g.lvl : 0;
+      s_rows[warp] = nrows;
+    }
+  }
+  __syncthreads();
+  for (int slot = 0; slot < ipw && k0 + slot < p.K; ++slot) {
+    const int k = k0 + slot;
+    const int run = s_run[slot], nrows = s_rows[slot];
+    const WarpTables<7>& tb = tbs[slot];
+    const int c0 = warp * WI::kChannels;
+    const LvParam& lv = p.lv[s_lvl[slot]];
+    if (lane == 0) bulk_wait_read_all();  // the previous item's bulk store has finished reading the tile
+    __syncwarp();
+    if (run < 0) {
+      for (int j = lane; j < WI::kTileFloats; j += 32) tile[j] = 0.f;
+    } else {
+      const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)s_b[slot] * lv.sn + c0 + 2 * lane);
+      const uint32_t swb = (uint32_t)lv.sw * 4u;
+      if (nrows >= 0 && run <= 3) roi_warp_body_rm<3, ROWS, CSW>(tb, nrows, fb, swb, my);
+      else if (nrows >= 0) roi_warp_body_rm<4, 1, CSW>(tb, nrows, fb, swb, my);
+      else if (run <= 3) roi_warp_body<7, 7, 3, CSW>(tb, 0, fb, swb, my);
+      else if (run == 4) roi_warp_body<7, 7, 4, CSW>(tb, 0, fb, swb, my);
+      else roi_warp_body<7, 7, 0, CSW>(tb, 0, fb, swb, my);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      float* dst = out + ((size_t)k * p.C + c0) * PP;
+      const uint32_t bytes = (uint32_t)(WI::kChannels * PP * sizeof(float));
+      if (flags & 1) bulk_store_smem_to_global_hint(dst, tile, bytes, pol);
+      else bulk_store_smem_to_global(dst, tile, bytes);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read_all();
+}
+
 // ---- backward -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
@@ -1675,6 +1891,38 @@ static int launch_fwd_staged(const RoiParams& p, float* out, cudaStream_t st, in
   kern<<<(unsigned)want, (WARPS + 2) * 32, smem, st>>>(p, out, rpc, flags, (uint32_t)ring);
   return after_launch();
 }
+
+// row-major forward: P = 7, C == 256 (a RoI = the CTA's four 64-channel warps), NHWC with 16-byte aligned rows
+static bool rm_eligible(const RoiParams& p) {
+  if (p.PH != 7 || p.C != 256) return false;
+  for (int l = 0; l < p.L; ++l) {
+    const LvParam& v = p.lv[l];
+    if (v.W < 4 || v.sh % 4 != 0 || (long long)v.H * v.sh * 4 >= (1ll << 31)) return false;
+  }
+  return true;
+}
+
+template <int ROWS, int CSW>
+static int launch_fwd_rm(const RoiParams& p, float* out, cudaStream_t st) {
+  using WI = WarpItem<7, 7>;
+  constexpr int WARPS = 4;
+  const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<7>);
+  int ipw = p.K >= 2 * 4 * sm_count() ? 2 : 1;
+  if (const char* v = tune_get("LCR_ROI_IPW")) ipw = atoi(v) >= 1 && atoi(v) <= WARPS ? atoi(v) : ipw;
+  const long long want = ((long long)p.K + ipw - 1) / ipw;
+  LCR_REQUIRE(want < (1ll << 31), LCR_ERR_CAPACITY);
+  auto kern = roi_fwd_rm_kernel<ROWS, CSW>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    configured_dev = dev;
+  }
+  kern<<<(unsigned)want, WARPS * 32, smem, st>>>(p, out, tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1, ipw);
+  return after_launch();
+}
 }  // namespace lcr
 
 using namespace lcr;
@@ -1697,6 +1945,11 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
       const int flags = (tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (tune_is("LCR_ROI_FWD", "staged_direct") ? 4 : 0);
       if (tune_is("LCR_ROI_STAGED_WARPS", "4")) return p.C == 256 ? launch_fwd_staged<7, 256>(p, out, st, flags) : launch_fwd_staged<7, 0>(p, out, st, flags);
       return p.C == 256 ? launch_fwd_staged<4, 256>(p, out, st, flags) : launch_fwd_staged<4, 0>(p, out, st, flags);
+    }
+    if (rm_eligible(p) && (tune_is("LCR_ROI_FWD", "rm") || tune_is("LCR_ROI_FWD", "rm1"))) {
+      const bool two = tune_is("LCR_ROI_FWD", "rm");
+      if (all_sw_equal(p, 256)) return two ? launch_fwd_rm<2, 256>(p, out, st) : launch_fwd_rm<1, 256>(p, out, st);
+      return two ? launch_fwd_rm<2, 0>(p, out, st) : launch_fwd_rm<1, 0>(p, out, st);
     }
     if (warp_eligible(p) && !tune_is("LCR_ROI_FWD", "cta")) {
       // (P = 7 with 32-channel items — half-warps taking x-bins 0-3 / 4-6, XB = 4, 6 CTAs/SM instead of 4 — was measured

@@ -265,3 +265,40 @@ def test_abi_rejects_non_dense_zero_fill_and_ignores_bad_levels(ops, synth):
     gref = torch.zeros_like(feat)
     ops.roi_align_bwd(T(np.ones_like(out[good])), [gref], [0.25], T(r[good]), T(lv[good]), 2, False, zero_grad=True)
     assert torch.allclose(gin, gref, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("variant", ["rm", "rm1"])
+@pytest.mark.parametrize("K,mode,levels", [(600, "anchor", 1), (41, "anchor", 1), (2500, "fpn", 4)])
+def test_row_major_forward(ops, synth, oracle, tune, variant, K, mode, levels):
+    """roi_fwd_rm_kernel (row program: distinct window rows with pre-added y weights into three rotating accumulator sets;
+    rm = two rows' loads in flight per phase, rm1 = one): within 1e-5 of the oracle ELEMENTWISE (pooled-magnitude bound) and
+    within fp32 rounding of the warp kernel; edge cases, padding rows, multi-level lists and RoIs that fall back to the
+    sample walk (tiny / tall / wide) included."""
+    from gpu_util import N, T, nhwc, assert_close_elementwise
+    B, H, W, C = 2, 520, 704, 256
+    rois = synth.make_rois(K, 700 + K, img_h=H, img_w=W, mode=mode, batch=B, edge_cases=True)
+    rois[K // 3, 0] = -1.0
+    rois[K // 2, 1:] = [300.0, 200.0, 306.0, 204.0]                  # 1.5 x 1 feature px: bins far below one pixel (fallback)
+    rois[K // 2 + 1, 1:] = [10.0, 5.0, 60.0, 515.0]                  # 128 feature rows tall (fallback: > 32 rows)
+    feats, scales = [], []
+    for l in range(levels):
+        h, w = -(-H // (4 << l)), -(-W // (4 << l))
+        feats.append(synth.make_features(B, C, h, w, seed=80 + l))
+        scales.append(1.0 / (4 << l))
+    lv = None if levels == 1 else oracle.level_map(rois[:, 1:], 2, 1 + levels, 224.0, 4).astype(np.int32)
+    fd = [nhwc(T(f)) for f in feats]
+    lvd = None if lv is None else T(lv)
+    tune(LCR_ROI_FWD=None)
+    ref = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
+    tune(LCR_ROI_FWD=variant)
+    got = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 2e-6 * scale, np.abs(got - ref).max() / scale
+    tune(LCR_ROI_IPW="1")
+    assert np.array_equal(N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False)), got)
+    if K <= 600:
+        live = rois[:, 0] >= 0
+        want = oracle.roi_align_fwd(feats[0], rois[live], 7, 7, scales[0], 2, False)
+        mag = oracle.roi_align_fwd(np.abs(feats[0]), rois[live], 7, 7, scales[0], 2, False)
+        assert_close_elementwise(got[live], want, mag, RTOL, f"forward[{variant}]")
+        assert not got[~live].any()

@@ -79,13 +79,14 @@ def main():
         ref = None
         S = {"LCR_ROI_FWD": "staged"}
         for name, env in [("warp,ipw2 (default)", {}),
+                          ("row-major, 2 rows per phase (rm)", {"LCR_ROI_FWD": "rm"}),
+                          ("row-major, 1 row per phase (rm1)", {"LCR_ROI_FWD": "rm1"}),
+                          ("row-major rm, ipw1", {"LCR_ROI_FWD": "rm", "LCR_ROI_IPW": "1"}),
+                          ("row-major rm, ipw3", {"LCR_ROI_FWD": "rm", "LCR_ROI_IPW": "3"}),
+                          ("row-major rm, ipw4", {"LCR_ROI_FWD": "rm", "LCR_ROI_IPW": "4"}),
                           ("staged: 8 pooling warps, ring 56 KB (2 CTAs/SM), rpc 8", S),
                           ("staged: 4 pooling warps, ring 56 KB", {**S, "LCR_ROI_STAGED_WARPS": "4"}),
-                          ("staged: 8 warps, ring 150 KB (1 CTA/SM)", {**S, "LCR_ROI_RING_KB": "150"}),
-                          ("staged: 8 warps, ring 150 KB, rpc 32", {**S, "LCR_ROI_RING_KB": "150", "LCR_ROI_RPC": "32"}),
-                          ("staged: 4 warps, ring 150 KB, rpc 32", {**S, "LCR_ROI_RING_KB": "150", "LCR_ROI_RPC": "32", "LCR_ROI_STAGED_WARPS": "4"}),
-                          ("staged: 8 warps, ring 100 KB, rpc 16", {**S, "LCR_ROI_RING_KB": "100", "LCR_ROI_RPC": "16"}),
-                          ("staged: 8 warps, ring 56 KB, rpc 4", {**S, "LCR_ROI_RPC": "4"}),
+                          ("staged: 4 warps, ring 150 KB (1 CTA/SM), rpc 32", {**S, "LCR_ROI_RING_KB": "150", "LCR_ROI_RPC": "32", "LCR_ROI_STAGED_WARPS": "4"}),
                           ("staged kernel, nothing staged (consumers gather)", {"LCR_ROI_FWD": "staged_direct"}),
                           ("warp,ipw2 (again)", {})]:
             setenv(env)

@@ -205,6 +205,17 @@ int lcr_level_map_f32(const float* boxes, int box_stride, int K, int k_min, int 
  * callee zero-fills them first (on `stream`) — that needs DENSE levels (NCHW-contiguous or channels_last strides, so that
  * the level is one run of N*C*H*W floats from `data`): anything else returns LCR_ERR_INVALID_ARG before touching memory.
  * ---------------------------------------------------------------------------------------------- */
+/* The `aligned` argument of lcr_roi_align_*_f32 is a flag word:
+ *   bit 0  LCR_ROI_ALIGNED     torchvision's `aligned` (half-pixel shift, no minimum RoI size)
+ *   bit 1  LCR_ROI_CPU_COORDS  round the sample coordinates as torchvision's CPU kernel does (every operation rounded).
+ *          Default (bit clear): as its CUDA kernel does — nvcc contracts `roi * spatial_scale - offset` and
+ *          `roi_start + ph * bin_size` into FMAs.  The reference executes the CUDA op on a GPU; torchvision's own two ops
+ *          differ by an ulp of the coordinate = up to ~2e-5 of the output range on white-noise features, and this library
+ *          agrees with the matching one to ~1.5e-7 (tools/roi_coord_rounding_exp.py).  The CPU-generated golden vectors and
+ *          the oracle's default use bit 1. */
+#define LCR_ROI_ALIGNED 1
+#define LCR_ROI_CPU_COORDS 2
+
 typedef struct LcrFeatLevel {
   float* data;               /* features (forward, read-only) or grad_input (backward, accumulated) */
   int N, H, W;

@@ -44,6 +44,8 @@ struct RoiParams {
   const float* rois;
   const int* roi_level;
   int L, C, K, PH, PW, sr, aligned;
+  int cpu_coords;  // 1: sample coordinates rounded like torchvision's CPU op (every operation rounded); 0: like its CUDA op
+                   // (nvcc contracts start + bin_index * bin_size, and roi * scale - 0.5, into FMAs)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -54,6 +56,7 @@ struct RoiGeom {
   int gw, gh;
   int b, lvl;
   bool live;
+  int cpu_coords;
 };
 
 __device__ __forceinline__ RoiGeom roi_geom(const RoiParams& p, int k) {
@@ -65,10 +68,18 @@ __device__ __forceinline__ RoiGeom roi_geom(const RoiParams& p, int k) {
   g.live = (bf >= 0.f) && g.lvl >= 0 && g.lvl < p.L && g.b < p.lv[g.lvl < 0 || g.lvl >= p.L ? 0 : g.lvl].N;
   const float scale = p.lv[g.live ? g.lvl : 0].scale;
   const float off = p.aligned ? 0.5f : 0.0f;
-  g.sw = __fsub_rn(__fmul_rn(__ldg(r + 1), scale), off);
-  g.sh = __fsub_rn(__fmul_rn(__ldg(r + 2), scale), off);
-  const float ew = __fsub_rn(__fmul_rn(__ldg(r + 3), scale), off);
-  const float eh = __fsub_rn(__fmul_rn(__ldg(r + 4), scale), off);
+  float ew, eh;
+  if (p.cpu_coords) {
+    g.sw = __fsub_rn(__fmul_rn(__ldg(r + 1), scale), off);
+    g.sh = __fsub_rn(__fmul_rn(__ldg(r + 2), scale), off);
+    ew = __fsub_rn(__fmul_rn(__ldg(r + 3), scale), off);
+    eh = __fsub_rn(__fmul_rn(__ldg(r + 4), scale), off);
+  } else {  // roi * spatial_scale - offset as one FMA (identical when offset == 0)
+    g.sw = __fmaf_rn(__ldg(r + 1), scale, -off);
+    g.sh = __fmaf_rn(__ldg(r + 2), scale, -off);
+    ew = __fmaf_rn(__ldg(r + 3), scale, -off);
+    eh = __fmaf_rn(__ldg(r + 4), scale, -off);
+  }
   float rw = __fsub_rn(ew, g.sw), rh = __fsub_rn(eh, g.sh);
   if (!p.aligned) {
     rw = fmaxf(rw, 1.0f);
@@ -78,13 +89,17 @@ __device__ __forceinline__ RoiGeom roi_geom(const RoiParams& p, int k) {
   g.bw = __fdiv_rn(rw, (float)p.PW);
   g.gh = p.sr > 0 ? p.sr : (int)ceilf(__fdiv_rn(rh, (float)p.PH));
   g.gw = p.sr > 0 ? p.sr : (int)ceilf(__fdiv_rn(rw, (float)p.PW));
+  g.cpu_coords = p.cpu_coords;
   return g;
 }
 
 // position of sample i of bin pbin: start + pbin*bin + (i+0.5)*bin/grid
-__device__ __forceinline__ float sample_pos(float start, int pbin, float bin, int i, int grid) {
-  return __fadd_rn(__fadd_rn(start, __fmul_rn((float)pbin, bin)),
-                   __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)grid));
+// cpu_coords: every operation rounded (torchvision's CPU op); otherwise start + pbin * bin is one FMA, as nvcc compiles
+// `roi_start + ph * bin_size + (iy + .5f) * bin_size / grid` in torchvision's CUDA kernel.  The two differ by an ulp of the
+// coordinate (~4e-6 feature px at x ~ 100), i.e. by up to ~2e-5 of the output range on white-noise features.
+__device__ __forceinline__ float sample_pos(float start, int pbin, float bin, int i, int grid, int cpu_coords) {
+  const float head = cpu_coords ? __fadd_rn(start, __fmul_rn((float)pbin, bin)) : __fmaf_rn((float)pbin, bin, start);
+  return __fadd_rn(head, __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)grid));
 }
 
 // 1-D half of make_tap(): neighbours lo/hi and weights (w_lo = 1 - frac, w_hi = frac).
@@ -125,11 +140,11 @@ __global__ void __launch_bounds__(256) roi_fwd_generic_kernel(const __grid_const
       for (int iy = 0; iy < g.gh; ++iy) {
         int yl, yh;
         float wyl, wyh;
-        if (!axis_tap(sample_pos(g.sh, ph, g.bh, iy, g.gh), lv.H, yl, yh, wyl, wyh)) continue;
+        if (!axis_tap(sample_pos(g.sh, ph, g.bh, iy, g.gh, p.cpu_coords), lv.H, yl, yh, wyl, wyh)) continue;
         for (int ix = 0; ix < g.gw; ++ix) {
           int xl, xh;
           float wxl, wxh;
-          if (!axis_tap(sample_pos(g.sw, pw, g.bw, ix, g.gw), lv.W, xl, xh, wxl, wxh)) continue;
+          if (!axis_tap(sample_pos(g.sw, pw, g.bw, ix, g.gw, p.cpu_coords), lv.W, xl, xh, wxl, wxh)) continue;
           float v = __fmul_rn(__fmul_rn(wyl, wxl), __ldg(f + yl * lv.sh + xl * lv.sw));
           v = __fadd_rn(v, __fmul_rn(__fmul_rn(wyl, wxh), __ldg(f + yl * lv.sh + xh * lv.sw)));
           v = __fadd_rn(v, __fmul_rn(__fmul_rn(wyh, wxl), __ldg(f + yh * lv.sh + xl * lv.sw)));
@@ -161,11 +176,11 @@ __global__ void __launch_bounds__(256) roi_bwd_generic_kernel(const __grid_const
     for (int iy = 0; iy < g.gh; ++iy) {
       int yl, yh;
       float wyl, wyh;
-      if (!axis_tap(sample_pos(g.sh, ph, g.bh, iy, g.gh), lv.H, yl, yh, wyl, wyh)) continue;
+      if (!axis_tap(sample_pos(g.sh, ph, g.bh, iy, g.gh, p.cpu_coords), lv.H, yl, yh, wyl, wyh)) continue;
       for (int ix = 0; ix < g.gw; ++ix) {
         int xl, xh;
         float wxl, wxh;
-        if (!axis_tap(sample_pos(g.sw, pw, g.bw, ix, g.gw), lv.W, xl, xh, wxl, wxh)) continue;
+        if (!axis_tap(sample_pos(g.sw, pw, g.bw, ix, g.gw, p.cpu_coords), lv.W, xl, xh, wxl, wxh)) continue;
         atomicAdd(f + yl * lv.sh + xl * lv.sw, __fdiv_rn(__fmul_rn(go, __fmul_rn(wyl, wxl)), count));
         atomicAdd(f + yl * lv.sh + xh * lv.sw, __fdiv_rn(__fmul_rn(go, __fmul_rn(wyl, wxh)), count));
         atomicAdd(f + yh * lv.sh + xl * lv.sw, __fdiv_rn(__fmul_rn(go, __fmul_rn(wyh, wxl)), count));
@@ -202,11 +217,11 @@ __device__ __forceinline__ void build_tables(RoiTables<P>& tb, const RoiGeom& g,
   if (tid < 2 * P) {
     int lo, hi;
     float wl, wh;
-    bool ok = axis_tap(sample_pos(g.sw, tid >> 1, g.bw, tid & 1, 2), lv.W, lo, hi, wl, wh);
+    bool ok = axis_tap(sample_pos(g.sw, tid >> 1, g.bw, tid & 1, 2, g.cpu_coords), lv.W, lo, hi, wl, wh);
     tb.xs[tid] = AxisSample{(int)(lo * lv.sw), (int)(hi * lv.sw), wl, wh};
     tb.lo[0][tid] = ok ? lo : -1;
     tb.hi[0][tid] = hi;
-    ok = axis_tap(sample_pos(g.sh, tid >> 1, g.bh, tid & 1, 2), lv.H, lo, hi, wl, wh);
+    ok = axis_tap(sample_pos(g.sh, tid >> 1, g.bh, tid & 1, 2, g.cpu_coords), lv.H, lo, hi, wl, wh);
     tb.ys[tid] = AxisSample{(int)(lo * lv.sh), (int)(hi * lv.sh), wl, wh};
     tb.lo[1][tid] = ok ? lo : -1;
     tb.hi[1][tid] = hi;
@@ -413,11 +428,11 @@ __device__ __forceinline__ int build_tables_warp(WarpTables<P>& tb, const RoiGeo
   if (lane < 2 * P) {
     int lo, hi;
     float wl, wh;
-    bool ok = axis_tap(sample_pos(g.sw, lane >> 1, g.bw, lane & 1, 2), lv.W, lo, hi, wl, wh);
+    bool ok = axis_tap(sample_pos(g.sw, lane >> 1, g.bw, lane & 1, 2, g.cpu_coords), lv.W, lo, hi, wl, wh);
     tb.xs[lane] = AxisTapB{(uint32_t)(lo * lv.sw) * 4u, (uint32_t)(hi * lv.sw) * 4u, wl, wh};
     tb.lo[0][lane] = ok ? lo : -1;
     tb.hi[0][lane] = hi;
-    ok = axis_tap(sample_pos(g.sh, lane >> 1, g.bh, lane & 1, 2), lv.H, lo, hi, wl, wh);
+    ok = axis_tap(sample_pos(g.sh, lane >> 1, g.bh, lane & 1, 2, g.cpu_coords), lv.H, lo, hi, wl, wh);
     tb.ys[lane] = AxisTapB{(uint32_t)(lo * lv.sh) * 4u, (uint32_t)(hi * lv.sh) * 4u, wl, wh};
     tb.lo[1][lane] = ok ? lo : -1;
     tb.hi[1][lane] = hi;
@@ -1720,7 +1735,9 @@ static int fill_params(RoiParams& p, const LcrFeatLevel* lv, int L, int C, const
   }
   p.rois = rois;
   p.roi_level = roi_level;
-  p.L = L; p.C = C; p.K = K; p.PH = PH; p.PW = PW; p.sr = sr; p.aligned = aligned;
+  p.L = L; p.C = C; p.K = K; p.PH = PH; p.PW = PW; p.sr = sr;
+  p.aligned = aligned & 1;            // LCR_ROI_ALIGNED
+  p.cpu_coords = (aligned >> 1) & 1;  // LCR_ROI_CPU_COORDS
   return LCR_OK;
 }
 

@@ -70,7 +70,7 @@ at::Tensor boxes_to_rois(const std::vector<at::Tensor>& boxes) {
 
 struct RoIAlignFn : public torch::autograd::Function<RoIAlignFn> {
   static at::Tensor forward(torch::autograd::AutogradContext* ctx, const at::Tensor& input, const at::Tensor& rois_in,
-                            double scale, int64_t PH, int64_t PW, int64_t sr, bool aligned) {
+                            double scale, int64_t PH, int64_t PW, int64_t sr, int64_t flags) {
     TORCH_CHECK(input.is_cuda(), "liblcr ops need CUDA tensors: the region pipeline has no CPU fallback");
     TORCH_CHECK(input.dim() == 4, "roi_align: input must be [N, C, H, W]");
     const c10::cuda::CUDAGuard guard(input.device());
@@ -92,14 +92,14 @@ struct RoIAlignFn : public torch::autograd::Function<RoIAlignFn> {
     if (K > 0) {
       const LcrFeatLevel lv = level_of(feat, scale);
       check_rc(lcr_roi_align_fwd_f32(&lv, 1, (int)C, rois.data_ptr<float>(), nullptr, (int)K, (int)PH, (int)PW, (int)sr,
-                                     aligned ? 1 : 0, out.data_ptr<float>(), current_stream()),
+                                     (int)flags, out.data_ptr<float>(), current_stream()),
                "roi_align_fwd");
     }
     ctx->save_for_backward({rois});
     ctx->saved_data["shape"] = std::vector<int64_t>{N, C, H, W};
     ctx->saved_data["scale"] = scale;
     ctx->saved_data["sr"] = sr;
-    ctx->saved_data["aligned"] = aligned;
+    ctx->saved_data["flags"] = flags;   // bit 0 aligned, bit 1 CPU-op coordinate rounding (include/lcr.h)
     return out;
   }
 
@@ -115,20 +115,20 @@ struct RoIAlignFn : public torch::autograd::Function<RoIAlignFn> {
     at::Tensor gin = at::empty_strided({N, C, H, W}, {H * W * C, 1, W * C, C}, g.options());
     const LcrFeatLevel lv = level_of(gin, ctx->saved_data["scale"].toDouble());
     check_rc(lcr_roi_align_bwd_f32(K > 0 ? g.data_ptr<float>() : nullptr, &lv, 1, (int)C, rois.data_ptr<float>(), nullptr, (int)K,
-                                   (int)PH, (int)PW, (int)ctx->saved_data["sr"].toInt(), ctx->saved_data["aligned"].toBool() ? 1 : 0,
+                                   (int)PH, (int)PW, (int)ctx->saved_data["sr"].toInt(), (int)ctx->saved_data["flags"].toInt(),
                                    /*zero_grad=*/1, current_stream()),
              "roi_align_bwd");
     return {gin, at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor()};
   }
 };
 
-at::Tensor roi_align(const at::Tensor& input, const at::Tensor& rois, double scale, int64_t PH, int64_t PW, int64_t sr, bool aligned) {
-  return RoIAlignFn::apply(input, rois, scale, PH, PW, sr < 0 ? 0 : sr, aligned);
+at::Tensor roi_align(const at::Tensor& input, const at::Tensor& rois, double scale, int64_t PH, int64_t PW, int64_t sr, int64_t flags) {
+  return RoIAlignFn::apply(input, rois, scale, PH, PW, sr < 0 ? 0 : sr, flags);
 }
 
 at::Tensor roi_align_list(const at::Tensor& input, const std::vector<at::Tensor>& boxes, double scale, int64_t PH, int64_t PW,
-                          int64_t sr, bool aligned) {
-  return RoIAlignFn::apply(input, boxes_to_rois(boxes), scale, PH, PW, sr < 0 ? 0 : sr, aligned);
+                          int64_t sr, int64_t flags) {
+  return RoIAlignFn::apply(input, boxes_to_rois(boxes), scale, PH, PW, sr < 0 ? 0 : sr, flags);
 }
 
 // torchvision.ops.nms: int64 indices of the kept boxes in decreasing score order.  One host sync (the dense return

@@ -15,6 +15,29 @@ from ._lib import LcrFeatLevel, LcrRpnCfg, LcrRpnLevel, check
 
 XFORM_CLIP = math.log(1000.0 / 16)
 
+# RoIAlign sample-coordinate rounding: "cuda" (default) = as torchvision's CUDA op, the op the reference executes on a GPU
+# (nvcc contracts `roi_start + ph * bin_size` into an FMA); "cpu" = as torchvision's CPU op (every operation rounded), the rule
+# of the CPU-generated golden vectors and of the oracle.  torchvision's own two ops differ by up to ~2e-5 of the output range
+# on white-noise features; with the matching rule this library agrees with either to ~1.5e-7 (tools/roi_coord_rounding_exp.py).
+_roi_cpu_coords = False
+
+
+def set_roi_coord_rule(rule: str) -> str:
+    """'cuda' (default) or 'cpu'; returns the previous rule."""
+    global _roi_cpu_coords
+    if rule not in ("cuda", "cpu"):
+        raise ValueError("rule must be 'cuda' or 'cpu'")
+    prev = "cpu" if _roi_cpu_coords else "cuda"
+    _roi_cpu_coords = rule == "cpu"
+    return prev
+
+
+def roi_align_flags(aligned: bool, cpu_coords: Optional[bool] = None) -> int:
+    """The `aligned` flag word of lcr_roi_align_*_f32: bit 0 aligned, bit 1 CPU-op coordinate rounding."""
+    cc = _roi_cpu_coords if cpu_coords is None else bool(cpu_coords)
+    return (1 if aligned else 0) | (2 if cc else 0)
+
+
 _workspaces: dict = {}
 _retired: list = []      # outgrown workspaces: kept alive, a CUDA graph captured earlier may still point into them
 
@@ -338,7 +361,7 @@ def _dense(f: torch.Tensor) -> bool:
 
 def roi_align_fwd(feats: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
                   roi_level: Optional[torch.Tensor], output_size, sampling_ratio: int, aligned: bool,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, cpu_coords: Optional[bool] = None) -> torch.Tensor:
     """a9/a11 — RoIAlign forward over one or several levels.  feats: logical [N,C,H,W] fp32 tensors
     (NCHW-contiguous or channels_last; other stridings are copied).  rois [K,5].  `out`: optional
     caller-owned contiguous fp32 buffer of at least K*C*PH*PW elements (a serving loop reuses it)."""
@@ -358,13 +381,15 @@ def roi_align_fwd(feats: Sequence[torch.Tensor], scales: Sequence[float], rois: 
     lvl = None if roi_level is None else roi_level.to(torch.int32).contiguous()
     with _dev(r.device):
         check(_lib.load().lcr_roi_align_fwd_f32(_feat_levels(feats, scales), len(feats), Cc, r.data_ptr(), _ptr(lvl), K, PH, PW,
-                                                int(sampling_ratio), 1 if aligned else 0, out.data_ptr(), _stream()),
+                                                int(sampling_ratio), roi_align_flags(aligned, cpu_coords), out.data_ptr(),
+                                                _stream()),
               "roi_align_fwd")
     return out
 
 
 def roi_align_bwd(grad_out: torch.Tensor, grads: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
-                  roi_level: Optional[torch.Tensor], sampling_ratio: int, aligned: bool, zero_grad: bool = True) -> None:
+                  roi_level: Optional[torch.Tensor], sampling_ratio: int, aligned: bool, zero_grad: bool = True,
+                  cpu_coords: Optional[bool] = None) -> None:
     """a10 — RoIAlign backward: accumulates into `grads` (dense NCHW or channels_last tensors of the
     forward feature shapes), zero-filling them first when zero_grad."""
     g = _f32c(grad_out)
@@ -377,8 +402,8 @@ def roi_align_bwd(grad_out: torch.Tensor, grads: Sequence[torch.Tensor], scales:
     lvl = None if roi_level is None else roi_level.to(torch.int32).contiguous()
     with _dev(g.device):
         check(_lib.load().lcr_roi_align_bwd_f32(g.data_ptr(), _feat_levels(grads, scales), len(grads), Cc, r.data_ptr(), _ptr(lvl),
-                                                K, PH, PW, int(sampling_ratio), 1 if aligned else 0, 1 if zero_grad else 0,
-                                                _stream()), "roi_align_bwd")
+                                                K, PH, PW, int(sampling_ratio), roi_align_flags(aligned, cpu_coords),
+                                                1 if zero_grad else 0, _stream()), "roi_align_bwd")
 
 
 def paste_masks(probs: torch.Tensor, boxes: torch.Tensor, img_h: int, img_w: int, threshold: float = 0.5,

@@ -84,9 +84,10 @@ def roi_align(input: torch.Tensor, boxes, output_size, spatial_scale: float = 1.
         raise _lib.LcrError("liblcr ops need CUDA tensors: the region pipeline has no CPU fallback")
     ext = _ext.load()
     if ext is not None:  # C++ call path + C++ autograd node (csrc/torch_ext.cpp): same kernels, no Python plumbing
+        flags = ops.roi_align_flags(bool(aligned))       # bit 0 aligned, bit 1 CPU-op coordinate rounding (ops.set_roi_coord_rule)
         if isinstance(boxes, (list, tuple)):
-            return ext.roi_align_list(input, list(boxes), float(spatial_scale), output_size[0], output_size[1], sr, bool(aligned))
-        return ext.roi_align(input, boxes, float(spatial_scale), output_size[0], output_size[1], sr, bool(aligned))
+            return ext.roi_align_list(input, list(boxes), float(spatial_scale), output_size[0], output_size[1], sr, flags)
+        return ext.roi_align(input, boxes, float(spatial_scale), output_size[0], output_size[1], sr, flags)
     rois = _as_rois(boxes)
     return _RoIAlignFn.apply(((float(spatial_scale),), rois, None, tuple(output_size), sr, bool(aligned)), input)
 

@@ -291,11 +291,28 @@ void orc_level_map(const float* boxes, int box_stride, int K, int k_min, int k_m
  * ------------------------------------------------------------------------------------------- */
 typedef struct { int yl, yh, xl, xh; float w1, w2, w3, w4; int valid; } Tap;
 
-static void roi_geometry(const float* roi, float scale, int aligned, int PH, int PW, int sr, float* sw,
+/* `aligned` is a flag word: bit 0 = torchvision's aligned, bit 1 = the sample coordinates are rounded as torchvision's CUDA
+ * kernel rounds them (nvcc contracts `roi * spatial_scale - offset` and `roi_start + ph * bin_size` into FMAs) instead of as
+ * its CPU kernel does (every operation rounded).  The two ops of the same torchvision differ by an ulp of the coordinate,
+ * i.e. by up to ~2e-5 of the output range on white-noise features (measured on the B200: tools/roi_coord_rounding_exp.py);
+ * the golden vectors are CPU-generated (bit 1 clear), the reference on a GPU runs the CUDA op (bit 1 set). */
+static inline float sample_coord(float start, int bin_index, float bin, int i, int grid, int cuda_coords) {
+  const float head = cuda_coords ? fmaf((float)bin_index, bin, start) : start + (float)bin_index * bin;
+  return head + ((float)i + 0.5f) * bin / (float)grid;
+}
+
+static void roi_geometry(const float* roi, float scale, int aligned_flags, int PH, int PW, int sr, float* sw,
                          float* sh, float* bw, float* bh, int* gh, int* gw) {
+  const int aligned = aligned_flags & 1, cuda_coords = (aligned_flags >> 1) & 1;
   const float off = aligned ? 0.5f : 0.0f;
-  *sw = roi[1] * scale - off; *sh = roi[2] * scale - off;
-  const float ew = roi[3] * scale - off, eh = roi[4] * scale - off;
+  float ew, eh;
+  if (cuda_coords) {
+    *sw = fmaf(roi[1], scale, -off); *sh = fmaf(roi[2], scale, -off);
+    ew = fmaf(roi[3], scale, -off); eh = fmaf(roi[4], scale, -off);
+  } else {
+    *sw = roi[1] * scale - off; *sh = roi[2] * scale - off;
+    ew = roi[3] * scale - off; eh = roi[4] * scale - off;
+  }
   float rw = ew - *sw, rh = eh - *sh;
   if (!aligned) { rw = rw > 1.f ? rw : 1.f; rh = rh > 1.f ? rh : 1.f; }
   *bh = rh / (float)PH; *bw = rw / (float)PW;
@@ -334,9 +351,9 @@ void orc_roi_align_fwd(const float* feat, int N, int C, int H, int W, int64_t sn
       for (int pw = 0; pw < PW; ++pw) {
         for (int c = 0; c < C; ++c) o[((size_t)c * PH + ph) * PW + pw] = 0.f;
         for (int iy = 0; iy < gh; ++iy) {
-          const float y = sh + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
+          const float y = sample_coord(sh, ph, bh, iy, gh, (aligned >> 1) & 1);
           for (int ix = 0; ix < gw; ++ix) {
-            const float x = sw + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
+            const float x = sample_coord(sw, pw, bw, ix, gw, (aligned >> 1) & 1);
             const Tap t = make_tap(y, x, H, W);
             if (!t.valid) continue;
             for (int c = 0; c < C; ++c) {
@@ -373,9 +390,9 @@ void orc_roi_align_bwd(const float* grad_out, int N, int C, int H, int W, int64_
     for (int ph = 0; ph < PH; ++ph)
       for (int pw = 0; pw < PW; ++pw)
         for (int iy = 0; iy < gh; ++iy) {
-          const float y = sh + (float)ph * bh + ((float)iy + 0.5f) * bh / (float)gh;
+          const float y = sample_coord(sh, ph, bh, iy, gh, (aligned >> 1) & 1);
           for (int ix = 0; ix < gw; ++ix) {
-            const float x = sw + (float)pw * bw + ((float)ix + 0.5f) * bw / (float)gw;
+            const float x = sample_coord(sw, pw, bw, ix, gw, (aligned >> 1) & 1);
             const Tap t = make_tap(y, x, H, W);
             if (!t.valid) continue;
             for (int c = 0; c < C; ++c) {

@@ -191,8 +191,9 @@ def _strides(feat_shape, nhwc: bool):
     return (Cc * H * W, H * W, W, 1)
 
 
-def roi_align_fwd(feat, rois, PH=7, PW=7, scale=0.25, sampling_ratio=2, aligned=False) -> np.ndarray:
-    """feat: logical [N,C,H,W] numpy array (any strides are honoured through a contiguous copy)."""
+def roi_align_fwd(feat, rois, PH=7, PW=7, scale=0.25, sampling_ratio=2, aligned=False, cuda_coords=False) -> np.ndarray:
+    """feat: logical [N,C,H,W] numpy array (any strides are honoured through a contiguous copy).
+    cuda_coords: round the sample coordinates as torchvision's CUDA op does (FMA-contracted) instead of its CPU op."""
     f = _f32(feat)
     N, Cc, H, W = f.shape
     r = _f32(rois).reshape(-1, 5)
@@ -201,11 +202,12 @@ def roi_align_fwd(feat, rois, PH=7, PW=7, scale=0.25, sampling_ratio=2, aligned=
     sn, sc, sh, sw = _strides(f.shape, False)
     lib().orc_roi_align_fwd(_p(f), C.c_int(N), C.c_int(Cc), C.c_int(H), C.c_int(W), C.c_int64(sn), C.c_int64(sc),
                             C.c_int64(sh), C.c_int64(sw), _p(r), C.c_int(K), C.c_int(PH), C.c_int(PW),
-                            C.c_float(scale), C.c_int(sampling_ratio), C.c_int(1 if aligned else 0), _p(out))
+                            C.c_float(scale), C.c_int(sampling_ratio), C.c_int((1 if aligned else 0) | (2 if cuda_coords else 0)),
+                            _p(out))
     return out
 
 
-def roi_align_bwd(grad_out, rois, feat_shape, scale=0.25, sampling_ratio=2, aligned=False) -> np.ndarray:
+def roi_align_bwd(grad_out, rois, feat_shape, scale=0.25, sampling_ratio=2, aligned=False, cuda_coords=False) -> np.ndarray:
     g = _f32(grad_out)
     K, Cc, PH, PW = g.shape
     N, C2, H, W = feat_shape
@@ -215,11 +217,12 @@ def roi_align_bwd(grad_out, rois, feat_shape, scale=0.25, sampling_ratio=2, alig
     sn, sc, sh, sw = _strides(gi.shape, False)
     lib().orc_roi_align_bwd(_p(g), C.c_int(N), C.c_int(Cc), C.c_int(H), C.c_int(W), C.c_int64(sn), C.c_int64(sc),
                             C.c_int64(sh), C.c_int64(sw), _p(r), C.c_int(K), C.c_int(PH), C.c_int(PW),
-                            C.c_float(scale), C.c_int(sampling_ratio), C.c_int(1 if aligned else 0), _p(gi))
+                            C.c_float(scale), C.c_int(sampling_ratio), C.c_int((1 if aligned else 0) | (2 if cuda_coords else 0)),
+                            _p(gi))
     return gi
 
 
-def multiscale_roi_align_fwd(feats, scales, rois, levels, PH=7, PW=7, sampling_ratio=2, aligned=False):
+def multiscale_roi_align_fwd(feats, scales, rois, levels, PH=7, PW=7, sampling_ratio=2, aligned=False, cuda_coords=False):
     """MultiScaleRoIAlign (TV:ops/poolers.py:147-227): per-level roi_align scattered to roi order."""
     r = _f32(rois).reshape(-1, 5)
     Cc = feats[0].shape[1]
@@ -227,7 +230,7 @@ def multiscale_roi_align_fwd(feats, scales, rois, levels, PH=7, PW=7, sampling_r
     for l, (f, s) in enumerate(zip(feats, scales)):
         sel = np.nonzero(np.asarray(levels) == l)[0]
         if sel.size:
-            out[sel] = roi_align_fwd(f, r[sel], PH, PW, s, sampling_ratio, aligned)
+            out[sel] = roi_align_fwd(f, r[sel], PH, PW, s, sampling_ratio, aligned, cuda_coords)
     return out
 
 

@@ -57,6 +57,16 @@ def tune():
         _lib.set_tuning(k, os.environ.get(k))
 
 
+@pytest.fixture
+def roi_cpu_coords():
+    """RoIAlign sample coordinates rounded as torchvision's CPU op rounds them — the rule of the CPU-generated golden vectors
+    and of the oracle's default — instead of the library default (torchvision's CUDA op, what the reference runs on a GPU)."""
+    from livecell_instance_segmentation_b200 import ops
+    prev = ops.set_roi_coord_rule("cpu")
+    yield
+    ops.set_roi_coord_rule(prev)
+
+
 def pytest_collection_modifyitems(config, items):
     """GPU tests are skipped (not failed) where no CUDA device exists."""
     try:

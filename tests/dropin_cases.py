@@ -219,7 +219,7 @@ class _Loader:
         return len(self.batches)
 
 
-def run_train_epoch(device, patched, n_batches=2, B=4, H=256, W=256, perturb=False):
+def run_train_epoch(device, patched, n_batches=2, B=4, H=256, W=256, perturb=False, perturb_seed=99):
     """train_custom.train_one_epoch + evaluate, imported UNCHANGED (stub matplotlib/wandb/pycocotools), driven with a
     synthetic loader (train_custom.py:21-166)."""
     _deterministic()
@@ -240,12 +240,32 @@ def run_train_epoch(device, patched, n_batches=2, B=4, H=256, W=256, perturb=Fal
         calibrate_rpn(model, torch.stack([i.to(device) for i in batches[0][0]]))
         if perturb:
             assert not patched
-            perturb_roi_align_by_one_ulp(model)
+            perturb_roi_align_by_one_ulp(model, perturb_seed)
+        # record, per training step, how many of the top-501 post-sigmoid scores collide (torch.topk's tie order is unspecified)
+        import sys as _sys
+        ties = []
+        wrapped = []
+        for mod_name in ("custom_maskrcnn", "src.custom_maskrcnn"):
+            mod = _sys.modules.get(mod_name)
+            if mod is None or not hasattr(mod, "generate_training_proposals"):
+                continue
+            inner = mod.generate_training_proposals
+
+            def spy(cls_scores, anchors, image_size, dev, *a, _inner=inner, **kw):
+                s_ = torch.sigmoid(cls_scores).permute(1, 2, 0).reshape(-1)
+                top = torch.topk(s_, min(501, s_.numel())).values
+                ties.append(int(top.numel() - torch.unique(top).numel()))
+                return _inner(cls_scores, anchors, image_size, dev, *a, **kw)
+
+            mod.generate_training_proposals = spy
+            wrapped.append((mod, inner))
         torch.manual_seed(4321)
         metrics = tc.train_one_epoch(model, _Loader(batches), opt, device, epoch=1)
         val = tc.evaluate(model, _Loader(batches[:1]), device)
+        for mod, inner in wrapped:
+            mod.generate_training_proposals = inner
         return {k: float(v) for k, v in metrics.items()}, {k: float(v) for k, v in val.items()}, \
-            {"roi_align_type": type(model.roi_align).__module__}
+            {"roi_align_type": type(model.roi_align).__module__, "topk_ties_per_step": ties}
     finally:
         if inst is not None:
             inst.uninstall()

@@ -152,17 +152,19 @@ def test_train_one_epoch_and_evaluate_run_unchanged():
     for k in keys:       # the gradient norm sums every parameter's backward (atomics, split-k reductions): 1e-4
         assert abs(mp[k] - ma[k]) <= (1e-4 if k == "gradient_norm_mean" else 1e-5) * max(abs(ma[k]), 1e-3), (k, ma[k], mp[k])
     # two batches: the second step runs on weights that went through an AdamW update (g/|g|-like on its first step, so
-    # sub-ulp gradient differences become lr-sized weight differences and can move a proposal across the top-k edge):
-    # compare against the untouched model's own run-to-run spread
-    m1, v1, _ = dc.run_train_epoch(DEV, False, n_batches=2)
-    m2, v2, _ = dc.run_train_epoch(DEV, False, n_batches=2, perturb=True)    # 1-ulp yardstick (dropin_cases.py)
-    m3, v3, _ = dc.run_train_epoch(DEV, True, n_batches=2)
+    # sub-ulp gradient differences become lr-sized weight differences).  Yardstick: the UNTOUCHED model with its pooled
+    # features perturbed by one ulp (three random sign patterns) — measured on the B200: loss_box_cls 0.643 untouched,
+    # 0.651-0.668 under five such perturbations, 0.669 patched (tools/dropin_epoch_spread.py).
+    m1, v1, i1 = dc.run_train_epoch(DEV, False, n_batches=2)
+    yard = [dc.run_train_epoch(DEV, False, n_batches=2, perturb=True, perturb_seed=sd)[0] for sd in (1, 2, 3)]
+    m3, v3, i3 = dc.run_train_epoch(DEV, True, n_batches=2)
     for k in keys:
-        spread = abs(m2[k] - m1[k])
-        assert abs(m3[k] - m1[k]) <= max(4 * spread, 5e-2 * max(abs(m1[k]), 1e-3)), (k, m1[k], m2[k], m3[k])
+        spread = max(abs(y[k] - m1[k]) for y in yard)
+        print(f"[dropin]   2-batch {k}: untouched {m1[k]:.6f}  1-ulp x3 {[round(y[k], 6) for y in yard]}  patched {m3[k]:.6f}")
+        assert abs(m3[k] - m1[k]) <= 2.0 * spread + 1e-3 * max(abs(m1[k]), 1e-3), (k, m1[k], [y[k] for y in yard], m3[k])
     assert v3["total_gt_instances"] == v1["total_gt_instances"]
+    print(f"[dropin] colliding scores among the top-501 per training step: untouched {i1['topk_ties_per_step']}, patched {i3['topk_ties_per_step']}")
     print(f"[dropin] train_one_epoch (1 batch): {mp}")
-    print(f"[dropin] train_one_epoch (2 batches) untouched {m1['total_loss']:.6f} / 1-ulp {m2['total_loss']:.6f}, patched {m3['total_loss']:.6f}")
 
 
 def test_gradio_predict_and_tile_stitching_run_unchanged(tmp_path):

@@ -7,7 +7,7 @@ import torch
 
 from gpu_util import N, T, assert_close_rel, nhwc
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("roi_cpu_coords")]   # oracle / golden = torchvision's CPU-op coordinate rule
 
 
 @pytest.fixture(scope="module")

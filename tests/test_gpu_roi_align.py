@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("roi_cpu_coords")]   # oracle / golden = torchvision's CPU-op coordinate rule
 
 RTOL = 1e-5   # north star: "RoIAlign forward/backward ... within 1e-5 relative error in fp32"
 
@@ -74,11 +74,16 @@ def test_c1_shape_vs_oracle_and_torchvision(ops, oracle, synth, P):
     gen = ops.roi_align_fwd([ft], [0.25], T(rois), None, (P, P), 2, False)
     assert_close_rel(N(fast), ref, RTOL)
     assert_close_rel(N(gen), ref, RTOL)
-    # torchvision's CUDA op itself deviates from its CPU op (the parity target) by up to ~2e-5 relative:
-    # nvcc contracts its sample-coordinate expression, and one ulp of a coordinate near 130 (1.5e-5) moves
-    # a bilinear weight by as much.  Cross-check only, at 1e-4.
+    # torchvision's CUDA op deviates from its CPU op by up to ~2e-5 relative: nvcc contracts its sample-coordinate
+    # expression into an FMA, and one ulp of a coordinate near 130 (1.5e-5) moves a bilinear weight by as much.  With the
+    # matching coordinate rule (the library default) the CUDA op is reproduced to fp32 rounding; the oracle can do both.
     tv = torchvision.ops.roi_align(ft, T(rois), (P, P), 0.25, 2, False)
     assert_close_rel(N(fast), N(tv), 1e-4)
+    fast_cuda = ops.roi_align_fwd([nhwc(ft)], [0.25], T(rois), None, (P, P), 2, False, cpu_coords=False)
+    gen_cuda = ops.roi_align_fwd([ft], [0.25], T(rois), None, (P, P), 2, False, cpu_coords=False)
+    assert_close_rel(N(fast_cuda), N(tv), 2e-6)
+    assert_close_rel(N(gen_cuda), N(tv), 2e-6)
+    assert_close_rel(N(fast_cuda), oracle.roi_align_fwd(feat, rois, P, P, 0.25, 2, False, cuda_coords=True), RTOL)
     # backward: all-ones grad, sum(grad_in) == sum(grad_out) for in-range RoIs
     inr = synth.make_rois(64, 7)
     gout = torch.ones((64, C, P, P), device="cuda:0")
@@ -302,3 +307,43 @@ def test_row_major_forward(ops, synth, oracle, tune, variant, K, mode, levels):
         mag = oracle.roi_align_fwd(np.abs(feats[0]), rois[live], 7, 7, scales[0], 2, False)
         assert_close_elementwise(got[live], want, mag, RTOL, f"forward[{variant}]")
         assert not got[~live].any()
+
+
+@pytest.mark.parametrize("P", [7, 14])
+def test_default_coordinate_rule_reproduces_torchvision_cuda(ops, oracle, synth, P):
+    """The library default rounds the sample coordinates as torchvision's CUDA kernel does (what the reference runs on a
+    GPU): forward and backward agree with torchvision's CUDA op to fp32 rounding on white-noise features at BASELINE C5 sizes
+    (where its CPU and CUDA ops differ from each other by ~1.7e-5 of the range), single- and multi-level, aligned and not."""
+    import torchvision
+    from gpu_util import N, T, nhwc
+    from livecell_instance_segmentation_b200 import ops as o
+    prev = o.set_roi_coord_rule("cuda")
+    try:
+        C, H, W, K = 256, 130, 176, 2048
+        g = torch.Generator(device="cuda:0").manual_seed(3)
+        feat = torch.randn((1, C, H, W), generator=g, device="cuda:0")
+        fn = nhwc(feat)
+        rois = T(synth.make_rois(K, 77, mode="anchor", edge_cases=True))
+        gout = torch.randn((K, C, P, P), generator=g, device="cuda:0")
+        for aligned in (False, True):
+            fr = feat.clone().requires_grad_(True)
+            tv = torchvision.ops.roi_align(fr, rois, (P, P), 0.25, 2, aligned)
+            tv.backward(gout)
+            scale, gscale = float(tv.abs().max()), float(fr.grad.abs().max())
+            for src in (fn, feat):                                  # fast NHWC kernels and the generic strided kernels
+                out = o.roi_align_fwd([src], [0.25], rois, None, (P, P), 2, aligned)
+                assert float((out - tv).abs().max()) <= 1e-6 * scale, (aligned, float((out - tv).abs().max()) / scale)
+                gin = torch.empty_like(src)
+                o.roi_align_bwd(gout, [gin], [0.25], rois, None, 2, aligned, zero_grad=True)
+                assert float((gin - fr.grad).abs().max()) <= 4e-6 * gscale, (aligned, float((gin - fr.grad).abs().max()) / gscale)
+            if not aligned:                                          # the other rule really is the other op
+                cpu_rule = o.roi_align_fwd([fn], [0.25], rois, None, (P, P), 2, False, cpu_coords=True)
+                assert float((cpu_rule - tv).abs().max()) > 3e-6 * scale
+        # the drop-in module and the C++ autograd node use the default rule
+        from livecell_instance_segmentation_b200.roi_align import RoIAlign
+        fr = feat.clone().requires_grad_(True)
+        y = RoIAlign((P, P), 0.25, 2)(fr, [rois[:200, 1:]])
+        tv = torchvision.ops.roi_align(feat, [rois[:200, 1:]], (P, P), 0.25, 2, False)
+        assert float((y - tv).abs().max()) <= 1e-6 * float(tv.abs().max())
+    finally:
+        o.set_roi_coord_rule(prev)

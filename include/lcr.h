@@ -144,7 +144,13 @@ int lcr_rpn_select_f32(const LcrRpnLevel* levels_host, int L, int B, const LcrRp
  *   - category != NULL: boxes only suppress boxes of the same category (batched_nms,
  *     TV:ops/boxes.py:51-120, per-class branch).
  *   - box j is suppressed by an earlier kept box i iff (double)IoU_fp32(i,j) > iou_threshold, with
- *     IoU = inter / (area_i + area_j - inter), no +1, NaN never suppresses.
+ *     IoU = inter / (area_i + area_j - inter), no +1, NaN never suppresses.  This is the comparison of
+ *     torchvision's CPU op (fp32 IoU against the double threshold).  Its CUDA op — what the reference
+ *     executes on a GPU — rounds the threshold to fp32 first; the two differ exactly when
+ *     IoU == (float)thr and (float)thr > thr (0.4f: yes; 0.5f: no), which anchor-grid boxes do produce.
+ *     A caller gets the CUDA op's rule by passing (double)(float)thr; the Python drop-ins (`nms`,
+ *     RegionPipeline, ops.nms_batched default) do that, `nms_cpu_rule` / cpu_threshold=True do not
+ *     (tests/test_gpu_nms.py::test_threshold_rule_matches_torchvision_cuda).
  * keep [S, post_n] i64: kept ORIGINAL in-segment indices in score order, truncated to post_n
  * (the keep_nms[:num_post_nms] of proposal_utils.py:56); keep_counts [S] i32.
  * ---------------------------------------------------------------------------------------------- */

@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kRankThreads) nms_rank_kernel(const float4* __
 // 2. mask build.  grid (spans, row_blocks, S), 256 threads = 8 warps.
 // CTA (span sp, row block rb): rows [32rb, 32rb+32), column words [32sp, 32sp+32).
 // ---------------------------------------------------------------------------------------------
-// torchvision compares the fp32 IoU with the threshold in DOUBLE.  For a float x and a double t,
+// torchvision's CPU op compares the fp32 IoU with the threshold in DOUBLE (its CUDA op rounds the threshold to fp32 first:
+// callers wanting that rule pass (double)(float)thr — see include/lcr.h).  For a float x and a double t,
 // (double)x > t  <=>  x > tf  with tf = the largest float whose double value is <= t (host side,
 // float_threshold()), so the kernel stays in fp32 — same decisions, no F2F.F64/DSETP per pair.
 // Disjoint pairs (inter == 0: IoU is 0 or NaN) can only "suppress" when tf < 0, which the

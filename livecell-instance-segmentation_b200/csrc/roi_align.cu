@@ -26,6 +26,8 @@
 // Roofline: HBM.  Algorithmic bytes fwd = 4*K*C*P*P (out) + unique feature bytes + 20*K.
 // Generic kernels (any strides / sampling ratio / pooled size) back every other configuration.
 #include <stdlib.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -775,7 +777,7 @@ struct __align__(16) RowOp {
 
 // Builds the row program of the warp's current RoI into tb.xs (free once the bins are folded: run <= 4) and returns the number
 // of rows (0: every sample is outside the map -> an all-zero tile), or -1 when the RoI does not qualify.  All lanes call.
-__device__ __forceinline__ int build_row_program(WarpTables<7>& tb, uint32_t shb, int lane) {
+__device__ __forceinline__ int build_row_program(WarpTables<7>& tb, uint32_t shb, int lane, int* span_out = nullptr) {
   constexpr uint32_t kAll = 0xffffffffu;
   const int ylo = lane < 14 ? tb.lo[1][lane] : -1, yhi = lane < 14 ? tb.hi[1][lane] : -1;
   const int rmin = __reduce_min_sync(kAll, ylo >= 0 ? ylo : 0x7fffffff);
@@ -783,40 +785,41 @@ __device__ __forceinline__ int build_row_program(WarpTables<7>& tb, uint32_t shb
   if (rmax < 0) return 0;
   if (rmax - rmin >= 32) return -1;
   const int r = rmin + lane;
-  float w[7];
-#pragma unroll
-  for (int ph = 0; ph < 7; ++ph) w[ph] = 0.f;
+  // Row r's weights for the (at most three) bin rows it feeds, accumulated in sample order exactly like a per-bin-row sum
+  // w[ph] += w_lo / 4; w[ph] += w_hi / 4 would be (zero terms are exact no-ops): pa = first bin row with a non-zero term,
+  // pb = last.  No per-lane array: nvcc puts a dynamically read w[7] into local memory (LDL/STL on the table build's
+  // critical path).
+  int pa = 7, pb = -1;
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
 #pragma unroll
   for (int t = 0; t < 14; ++t) {
     const int lo = tb.lo[1][t], hi = tb.hi[1][t];
     if (lo >= 0) {
       const AxisTapB s = tb.ys[t];
-      if (lo == r) w[t >> 1] += s.w_lo * 0.25f;
-      if (hi == r) w[t >> 1] += s.w_hi * 0.25f;
+      const float a = lo == r ? s.w_lo * 0.25f : 0.f;
+      const float b = hi == r ? s.w_hi * 0.25f : 0.f;
+      if (a != 0.f || b != 0.f) {
+        pa = min(pa, t >> 1);
+        pb = t >> 1;
+      }
+      const int d = (t >> 1) - pa;
+      w0 += d == 0 ? a : 0.f;
+      w0 += d == 0 ? b : 0.f;
+      w1 += d == 1 ? a : 0.f;
+      w1 += d == 1 ? b : 0.f;
+      w2 += d == 2 ? a : 0.f;
+      w2 += d == 2 ? b : 0.f;
     }
   }
-  int pa = 7, pb = -1;
-#pragma unroll
-  for (int ph = 0; ph < 7; ++ph)
-    if (w[ph] != 0.f) {
-      pa = min(pa, ph);
-      pb = ph;
-    }
   const bool used = pb >= 0 && r <= rmax;
   if (!__all_sync(kAll, !used || pb - pa <= 2)) return -1;
+  if (span_out) *span_out = __reduce_max_sync(kAll, used ? pb - pa : 0);  // 1: every row feeds at most two bin rows
   const uint32_t mask = __ballot_sync(kAll, used);
   // first bin rows must not decrease along the rows (they cannot for x2 >= x1 geometry; checked, not assumed)
   const uint32_t before = mask & ((1u << lane) - 1u);
   const int prev_pa = __shfl_sync(kAll, pa, before ? 31 - __clz(before) : lane);
   if (!__all_sync(kAll, !used || !before || prev_pa <= pa)) return -1;
   if (used) {
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-#pragma unroll
-    for (int ph = 0; ph < 7; ++ph) {
-      w0 = ph == pa ? w[ph] : w0;
-      w1 = ph == pa + 1 ? w[ph] : w1;
-      w2 = ph == pa + 2 ? w[ph] : w2;
-    }
     RowOp op;
     op.off_pa = ((uint32_t)r * shb) | (uint32_t)pa;
     op.w0 = w0;
@@ -966,6 +969,183 @@ __global__ void __launch_bounds__(128, ROWS == 2 ? 3 : 4)
       else bulk_store_smem_to_global(dst, tile, bytes);
       bulk_commit();
     }
+  }
+  if (lane == 0) bulk_wait_read_all();
+}
+
+// ---- forward, row program with PIPELINED rows (P = 7, C == 256): LCR_ROI_FWD=rmp ---------------------------------
+// ncu of roi_fwd_warp_kernel / roi_fwd_rm_kernel on the bench list (profiles/r02b_*): 39-45 % of all warp samples are
+// long-scoreboard stalls, two thirds of them on the FIRST FMUL2 of a window row — a warp issues a row's 21-28 loads, has
+// nothing else in flight, and sits through one loaded L2 round trip (~900 cycles) per row, ~12 rows per item.  Here the
+// row loop is software-pipelined WITHOUT extra registers: as soon as a bin's columns of row i have been multiplied into the
+// bin's x-pooled value, the same registers are re-loaded with the bin's columns of row i+1, so the next row's loads are in
+// flight during this row's remaining FMAs, the accumulator rotation and the tile stores, and a warp's wait per row shrinks
+// from (round trip) to (round trip - row compute).  The wait for the previous item's bulk store (tile reuse) moves from
+// the top of the item to the first tile write.
+template <int NB, int NACC, int CSW, bool XWREG>
+__device__ __forceinline__ void roi_warp_body_rmp(const WarpTables<7>& tb, int nrows, const char* __restrict__ fb, uint32_t swb,
+                                                  float* __restrict__ my, bool& store_pending) {
+  constexpr int P = 7, PP = 49;
+  const uint32_t cs = CSW ? (uint32_t)CSW * 4u : swb;
+  const RowOp* rows = reinterpret_cast<const RowOp*>(tb.xs);
+  uint32_t xo[P];
+  float2 acc0[P], acc1[P], acc2[P];
+  float xwr[P][XWREG ? NB : 1];
+#pragma unroll
+  for (int pw = 0; pw < P; ++pw) {
+    xo[pw] = tb.xoff[pw];
+    acc0[pw] = acc1[pw] = acc2[pw] = make_float2(0.f, 0.f);
+    if (XWREG) {
+      const float4 w = tb.xw[pw];
+      xwr[pw][0] = w.x;
+      if (NB > 1) xwr[pw][1 % NB] = w.y;
+      if (NB > 2) xwr[pw][2 % NB] = w.z;
+      if (NB > 3) xwr[pw][3 % NB] = w.w;
+    }
+  }
+  const bool lower = (threadIdx.x & 16) == 0;  // conflict-free tile stores, see roi_warp_body
+  float* const o_a = my + (lower ? 0 : PP);
+  float* const o_b = my + (lower ? PP : 0);
+  int base = 0;
+  auto retire = [&](int upto) {  // bin rows base .. upto-1 are complete: write them out and rotate the accumulator sets
+    if (base < upto && store_pending) {  // warp-uniform: the previous item's bulk store must have finished READING the tile
+      if ((threadIdx.x & 31) == 0) bulk_wait_read_all();
+      __syncwarp();
+      store_pending = false;
+    }
+    while (base < upto) {
+      const int o = base * P;
+#pragma unroll
+      for (int pw = 0; pw < P; ++pw) {
+        const float e = acc0[pw].x, f = acc0[pw].y;
+        o_a[o + pw] = lower ? e : f;
+        o_b[o + pw] = lower ? f : e;
+        acc0[pw] = acc1[pw];
+        if (NACC > 2) {
+          acc1[pw] = acc2[pw];
+          acc2[pw] = make_float2(0.f, 0.f);
+        } else {
+          acc1[pw] = make_float2(0.f, 0.f);
+        }
+      }
+      ++base;
+    }
+  };
+  float2 v[P][NB];
+  {
+    const char* row = fb + (rows[0].off_pa & ~7u);
+#pragma unroll
+    for (int pw = 0; pw < P; ++pw) {
+      const char* q = row + xo[pw];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) v[pw][j] = ldg_f2b(q + j * cs);
+    }
+  }
+#pragma unroll 1
+  for (int i = 0; i < nrows; ++i) {
+    const bool more = i + 1 < nrows;  // warp-uniform
+    const RowOp op = rows[i];
+    const char* nrow = fb + (rows[more ? i + 1 : i].off_pa & ~7u);
+    retire((int)(op.off_pa & 7u));
+    const float2 w0 = splat(op.w0), w1 = splat(op.w1), w2 = splat(op.w2);
+#pragma unroll
+    for (int pw = 0; pw < P; ++pw) {
+      float xw[4];
+      if (XWREG) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) xw[j] = xwr[pw][j];
+      } else {
+        const float4 xw4 = tb.xw[pw];
+        xw[0] = xw4.x; xw[1] = xw4.y; xw[2] = xw4.z; xw[3] = xw4.w;
+      }
+      float2 t = __fmul2_rn(splat(xw[0]), v[pw][0]);
+#pragma unroll
+      for (int j = 1; j < NB; ++j) t = ffma2(splat(xw[j]), v[pw][j], t);
+      if (more) {  // this bin's columns of the NEXT row, into the registers just consumed
+        const char* q = nrow + xo[pw];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) v[pw][j] = ldg_f2b(q + j * cs);
+      }
+      acc0[pw] = ffma2(w0, t, acc0[pw]);
+      acc1[pw] = ffma2(w1, t, acc1[pw]);
+      if (NACC > 2) acc2[pw] = ffma2(w2, t, acc2[pw]);
+    }
+  }
+  retire(P);
+}
+
+template <int CSW>
+__global__ void __launch_bounds__(128, 4)
+    roi_fwd_rmp_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out, int flags, int ipw) {
+  using WI = WarpItem<7, 7>;
+  constexpr int WARPS = 4, PP = 49;
+  constexpr uint32_t kAll = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = __shfl_sync(kAll, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * WI::kTileFloats;
+  WarpTables<7>* tbs = reinterpret_cast<WarpTables<7>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats);
+  __shared__ int s_run[WARPS], s_b[WARPS], s_lvl[WARPS], s_rows[WARPS], s_span[WARPS];
+  float* my = tile + (size_t)(2 * lane) * PP;
+  const uint64_t pol = l2_policy_evict_first();
+  const int k0 = blockIdx.x * ipw;
+  if (warp < ipw && k0 + warp < p.K) {
+    const RoiGeom g = roi_geom(p, k0 + warp);
+    const bool live = __any_sync(kAll, g.live);
+    int run = -1, nrows = -1, span = 2;
+    if (live) {
+      const LvParam& lv = p.lv[g.lvl];
+      run = build_tables_warp<7>(tbs[warp], g, lv, lane, 7);
+      if (run <= 4) nrows = build_row_program(tbs[warp], (uint32_t)lv.sh * 4u, lane, &span);
+    }
+    if (lane == 0) {
+      s_run[warp] = run;
+      s_b[warp] = g.b;
+      s_lvl[warp] = live ? g.lvl : 0;
+      s_rows[warp] = nrows;
+      s_span[warp] = span;
+    }
+  }
+  __syncthreads();
+  bool store_pending = false;
+  for (int slot = 0; slot < ipw && k0 + slot < p.K; ++slot) {
+    const int k = k0 + slot;
+    const int run = s_run[slot], nrows = s_rows[slot];
+    const WarpTables<7>& tb = tbs[slot];
+    const int c0 = warp * WI::kChannels;
+    const LvParam& lv = p.lv[s_lvl[slot]];
+    const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)s_b[slot] * lv.sn + c0 + 2 * lane);
+    const uint32_t swb = (uint32_t)lv.sw * 4u;
+    const bool two = s_span[slot] <= 1;  // every window row feeds at most two bin rows (bins at least one pixel tall)
+    if (nrows > 0 && run <= 3) {
+      if (two && !(flags & 4)) roi_warp_body_rmp<3, 2, CSW, true>(tb, nrows, fb, swb, my, store_pending);
+      else if (two) roi_warp_body_rmp<3, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending);
+      else roi_warp_body_rmp<3, 3, CSW, false>(tb, nrows, fb, swb, my, store_pending);
+    } else if (nrows > 0) {
+      if (two) roi_warp_body_rmp<4, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending);
+      else roi_warp_body_rmp<4, 3, CSW, false>(tb, nrows, fb, swb, my, store_pending);
+    } else {
+      if (store_pending) {
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+        store_pending = false;
+      }
+      if (run < 0 || nrows == 0) {  // padding row, or every sample outside the map
+        for (int j = lane; j < WI::kTileFloats; j += 32) tile[j] = 0.f;
+      } else if (run <= 3) roi_warp_body<7, 7, 3, CSW>(tb, 0, fb, swb, my);
+      else if (run == 4) roi_warp_body<7, 7, 4, CSW>(tb, 0, fb, swb, my);
+      else roi_warp_body<7, 7, 0, CSW>(tb, 0, fb, swb, my);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      float* dst = out + ((size_t)k * p.C + c0) * PP;
+      const uint32_t bytes = (uint32_t)(WI::kChannels * PP * sizeof(float));
+      if (flags & 1) bulk_store_smem_to_global_hint(dst, tile, bytes, pol);
+      else bulk_store_smem_to_global(dst, tile, bytes);
+      bulk_commit();
+    }
+    store_pending = true;
   }
   if (lane == 0) bulk_wait_read_all();
 }
@@ -1721,6 +1901,117 @@ __global__ void __launch_bounds__((256 / WarpItem<7, XB>::kChannels + 2) * 32, 2
   }
 }
 
+// ---- forward, persistent teams (P = 7, C == 256): LCR_ROI_FWD=team --------------------------------------------------
+// ncu of the launch-ordered kernels (profiles/r02b_*): a CTA lives for two RoIs; its table build (RoI load from DRAM, taps,
+// fold, row program: ~650 instructions on ONE warp's dependent chain) sits in front of a __syncthreads, so all four warps
+// spend 7-20 % of the CTA's life in it or waiting for it, then the CTA drains and the slot waits for the next launch.
+// Here ONE persistent CTA of 16 warps per SM (same 16 pooling warps, same 12.5 KB tile each; the per-CTA reserved shared
+// memory of four CTAs becomes room for 16 table slots) is split into four TEAMS of four warps (warp = 64-channel group).
+// A team pulls RoIs from a global counter IN ORDER (the RoIs in flight on the GPU stay ~600 consecutive list entries: the
+// L2 footprint of the launch-ordered grid, halved) through a ring of four table slots: warp w builds every fourth RoI's
+// tables TWO RoIs ahead of where it pools, hands them over on an mbarrier (full), and reuses the slot when all four warps
+// have released it (empty).  No block barrier: a warp that is building does not stop the other three, and the build costs
+// each warp a quarter of a build per item instead of a whole one per two items in front of a barrier.
+constexpr int kTeamSlots = 4;
+constexpr int kClaimSlots = 64;
+__device__ unsigned int g_roi_claim[kClaimSlots];
+
+struct TeamMeta {
+  int k, run, b, lvl, nrows, span;
+};
+
+template <int CSW>
+__global__ void __launch_bounds__(512, 1)
+    roi_fwd_team_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out, int flags, unsigned int* __restrict__ claim) {
+  using WI = WarpItem<7, 7>;
+  constexpr int TEAMS = 4, WARPS = 16, PP = 49;
+  constexpr uint32_t kAll = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = __shfl_sync(kAll, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int team = warp >> 2, w = warp & 3;
+  float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * WI::kTileFloats;
+  WarpTables<7>* tbs = reinterpret_cast<WarpTables<7>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats) + team * kTeamSlots;
+  __shared__ TeamMeta s_meta[TEAMS][kTeamSlots];
+  __shared__ __align__(8) uint64_t s_full[TEAMS][kTeamSlots], s_empty[TEAMS][kTeamSlots];
+  if (threadIdx.x < TEAMS * kTeamSlots) {
+    mbar_init(&s_full[0][0] + threadIdx.x, 1);
+    mbar_init(&s_empty[0][0] + threadIdx.x, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  float* my = tile + (size_t)(2 * lane) * PP;
+  const uint64_t pol = l2_policy_evict_first();
+  const int c0 = w * WI::kChannels;
+  bool store_pending = false;
+#pragma unroll 1
+  for (int i = -2;; ++i) {
+    const int j = i + 2;
+    if ((j & 3) == w) {  // this warp builds the team's RoI number j into slot w
+      if (j >= 4) mbar_wait(&s_empty[team][w], (uint32_t)(((j >> 2) - 1) & 1));
+      unsigned int kc = 0;
+      if (lane == 0) kc = atomicAdd(claim, 1u);
+      const int k = (int)min(__shfl_sync(kAll, kc, 0), (unsigned int)p.K);
+      int run = -1, nrows = -1, span = 2, gb = 0, glvl = 0;
+      if (k < p.K) {
+        const RoiGeom g = roi_geom(p, k);
+        const bool live = __any_sync(kAll, g.live);
+        gb = g.b;
+        if (live) {
+          glvl = g.lvl;
+          const LvParam& lv = p.lv[g.lvl];
+          run = build_tables_warp<7>(tbs[w], g, lv, lane, 7);
+          if (run <= 4) nrows = build_row_program(tbs[w], (uint32_t)lv.sh * 4u, lane, &span);
+        }
+      }
+      if (lane == 0) s_meta[team][w] = TeamMeta{k, run, gb, glvl, nrows, span};
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[team][w]);  // release: tables and header are visible to whoever observes the phase
+    }
+    if (i < 0) continue;
+    const int s = i & 3;
+    mbar_wait(&s_full[team][s], (uint32_t)((i >> 2) & 1));
+    const TeamMeta m = s_meta[team][s];
+    if (m.k >= p.K) break;  // the list is exhausted (team-uniform: every warp reads the same header)
+    const WarpTables<7>& tb = tbs[s];
+    const LvParam& lv = p.lv[m.lvl];
+    const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)m.b * lv.sn + c0 + 2 * lane);
+    const uint32_t swb = (uint32_t)lv.sw * 4u;
+    const bool two = m.span <= 1;
+    if (m.nrows > 0 && m.run <= 3) {
+      if (two && (flags & 4)) roi_warp_body_rmp<3, 2, CSW, true>(tb, m.nrows, fb, swb, my, store_pending);
+      else if (two) roi_warp_body_rmp<3, 2, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
+      else roi_warp_body_rmp<3, 3, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
+    } else if (m.nrows > 0) {
+      if (two) roi_warp_body_rmp<4, 2, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
+      else roi_warp_body_rmp<4, 3, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
+    } else {
+      if (store_pending) {
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+        store_pending = false;
+      }
+      if (m.run < 0 || m.nrows == 0) {  // padding row, or every sample outside the map
+        for (int q = lane; q < WI::kTileFloats; q += 32) tile[q] = 0.f;
+      } else if (m.run <= 3) roi_warp_body<7, 7, 3, CSW>(tb, 0, fb, swb, my);
+      else if (m.run == 4) roi_warp_body<7, 7, 4, CSW>(tb, 0, fb, swb, my);
+      else roi_warp_body<7, 7, 0, CSW>(tb, 0, fb, swb, my);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();  // the tile is complete and every lane is done with the table slot
+    if (lane == 0) {
+      mbar_arrive(&s_empty[team][s]);
+      float* dst = out + ((size_t)m.k * p.C + c0) * PP;
+      const uint32_t bytes = (uint32_t)(WI::kChannels * PP * sizeof(float));
+      if (flags & 1) bulk_store_smem_to_global_hint(dst, tile, bytes, pol);
+      else bulk_store_smem_to_global(dst, tile, bytes);
+      bulk_commit();
+    }
+    store_pending = true;
+  }
+  if (lane == 0) bulk_wait_read_all();
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1940,6 +2231,59 @@ static int launch_fwd_rm(const RoiParams& p, float* out, cudaStream_t st) {
   kern<<<(unsigned)want, WARPS * 32, smem, st>>>(p, out, tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1, ipw);
   return after_launch();
 }
+
+template <int CSW>
+static int launch_fwd_rmp(const RoiParams& p, float* out, cudaStream_t st) {
+  using WI = WarpItem<7, 7>;
+  constexpr int WARPS = 4;
+  const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<7>);
+  int ipw = p.K >= 2 * 4 * sm_count() ? 2 : 1;
+  if (const char* v = tune_get("LCR_ROI_IPW")) ipw = atoi(v) >= 1 && atoi(v) <= WARPS ? atoi(v) : ipw;
+  const long long want = ((long long)p.K + ipw - 1) / ipw;
+  LCR_REQUIRE(want < (1ll << 31), LCR_ERR_CAPACITY);
+  auto kern = roi_fwd_rmp_kernel<CSW>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    configured_dev = dev;
+  }
+  // flags: bit 0 = evict-first output stores, bit 2 = folded x weights re-read from shared memory instead of held in registers
+  const int flags = (tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (tune_is("LCR_ROI_XW", "smem") ? 4 : 0);
+  kern<<<(unsigned)want, WARPS * 32, smem, st>>>(p, out, flags, ipw);
+  return after_launch();
+}
+
+// persistent-team forward: rm_eligible + a list long enough to keep every team busy
+static int launch_fwd_team_impl(const RoiParams& p, float* out, cudaStream_t st, bool csw256) {
+  using WI = WarpItem<7, 7>;
+  constexpr int WARPS = 16;
+  const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + 4 * kTeamSlots * sizeof(WarpTables<7>);
+  static thread_local int configured_dev = -1;
+  static thread_local unsigned int* claim_base = nullptr;
+  static std::atomic<unsigned int> next_claim{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(roi_fwd_team_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_fwd_team_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaGetSymbolAddress(reinterpret_cast<void**>(&claim_base), g_roi_claim);
+    if (e != cudaSuccess) return cuda_status(e);
+    configured_dev = dev;
+  }
+  // one work counter per launch (launches in flight at the same time on different streams must not share one)
+  unsigned int* claim = claim_base + (next_claim.fetch_add(1, std::memory_order_relaxed) % kClaimSlots);
+  cudaError_t e = cudaMemsetAsync(claim, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return cuda_status(e);
+  // flags: bit 0 = evict-first output stores, bit 2 = folded x weights held in registers (NB = 3, two accumulator sets)
+  const int flags = (tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (tune_is("LCR_ROI_XW", "reg") ? 4 : 0);
+  const int grid = sm_count();
+  if (csw256) roi_fwd_team_kernel<256><<<grid, WARPS * 32, smem, st>>>(p, out, flags, claim);
+  else roi_fwd_team_kernel<0><<<grid, WARPS * 32, smem, st>>>(p, out, flags, claim);
+  return after_launch();
+}
 }  // namespace lcr
 
 using namespace lcr;
@@ -1963,6 +2307,8 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
       if (tune_is("LCR_ROI_STAGED_WARPS", "4")) return p.C == 256 ? launch_fwd_staged<7, 256>(p, out, st, flags) : launch_fwd_staged<7, 0>(p, out, st, flags);
       return p.C == 256 ? launch_fwd_staged<4, 256>(p, out, st, flags) : launch_fwd_staged<4, 0>(p, out, st, flags);
     }
+    if (rm_eligible(p) && tune_is("LCR_ROI_FWD", "team")) return launch_fwd_team_impl(p, out, st, all_sw_equal(p, 256));
+    if (rm_eligible(p) && tune_is("LCR_ROI_FWD", "rmp")) return all_sw_equal(p, 256) ? launch_fwd_rmp<256>(p, out, st) : launch_fwd_rmp<0>(p, out, st);
     if (rm_eligible(p) && (tune_is("LCR_ROI_FWD", "rm") || tune_is("LCR_ROI_FWD", "rm1"))) {
       const bool two = tune_is("LCR_ROI_FWD", "rm");
       if (all_sw_equal(p, 256)) return two ? launch_fwd_rm<2, 256>(p, out, st) : launch_fwd_rm<1, 256>(p, out, st);

@@ -272,7 +272,7 @@ def test_abi_rejects_non_dense_zero_fill_and_ignores_bad_levels(ops, synth):
     assert torch.allclose(gin, gref, rtol=0, atol=1e-5)
 
 
-@pytest.mark.parametrize("variant", ["rm", "rm1"])
+@pytest.mark.parametrize("variant", ["rm", "rm1", "rmp", "rmp_xwsmem", "team", "team_xwreg"])
 @pytest.mark.parametrize("K,mode,levels", [(600, "anchor", 1), (41, "anchor", 1), (2500, "fpn", 4)])
 def test_row_major_forward(ops, synth, oracle, tune, variant, K, mode, levels):
     """roi_fwd_rm_kernel (row program: distinct window rows with pre-added y weights into three rotating accumulator sets;
@@ -295,7 +295,12 @@ def test_row_major_forward(ops, synth, oracle, tune, variant, K, mode, levels):
     lvd = None if lv is None else T(lv)
     tune(LCR_ROI_FWD=None)
     ref = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
-    tune(LCR_ROI_FWD=variant)
+    if variant == "rmp_xwsmem":
+        tune(LCR_ROI_FWD="rmp", LCR_ROI_XW="smem")
+    elif variant == "team_xwreg":
+        tune(LCR_ROI_FWD="team", LCR_ROI_XW="reg")
+    else:
+        tune(LCR_ROI_FWD=variant)
     got = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
     scale = np.abs(ref).max()
     assert np.abs(got - ref).max() <= 2e-6 * scale, np.abs(got - ref).max() / scale

@@ -68,7 +68,7 @@ def main():
         print(json.dumps(kw), flush=True)
 
     def setenv(env):
-        for k in ("LCR_ROI_RING_KB", "LCR_ROI_STAGED_WARPS", "LCR_ROI_RPC", "LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_PASTE_CTAS", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
+        for k in ("LCR_ROI_XW", "LCR_ROI_RING_KB", "LCR_ROI_STAGED_WARPS", "LCR_ROI_RPC", "LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_PASTE_CTAS", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
                   "LCR_NMS_RESOLVE"):
             _lib.set_tuning(k, None)       # the library reads the environment only once: switches go through lcr_set_tuning
         for k, v in env.items():
@@ -79,6 +79,13 @@ def main():
         ref = None
         S = {"LCR_ROI_FWD": "staged"}
         for name, env in [("warp,ipw2 (default)", {}),
+                          ("persistent teams (team)", {"LCR_ROI_FWD": "team"}),
+                          ("persistent teams, x weights in registers", {"LCR_ROI_FWD": "team", "LCR_ROI_XW": "reg"}),
+                          ("row program, pipelined rows (rmp)", {"LCR_ROI_FWD": "rmp"}),
+                          ("rmp, x weights from shared memory", {"LCR_ROI_FWD": "rmp", "LCR_ROI_XW": "smem"}),
+                          ("rmp, ipw1", {"LCR_ROI_FWD": "rmp", "LCR_ROI_IPW": "1"}),
+                          ("rmp, ipw3", {"LCR_ROI_FWD": "rmp", "LCR_ROI_IPW": "3"}),
+                          ("rmp, ipw4", {"LCR_ROI_FWD": "rmp", "LCR_ROI_IPW": "4"}),
                           ("row-major, 2 rows per phase (rm)", {"LCR_ROI_FWD": "rm"}),
                           ("row-major, 1 row per phase (rm1)", {"LCR_ROI_FWD": "rm1"}),
                           ("row-major rm, ipw1", {"LCR_ROI_FWD": "rm", "LCR_ROI_IPW": "1"}),

@@ -1913,7 +1913,7 @@ __global__ void __launch_bounds__((256 / WarpItem<7, XB>::kChannels + 2) * 32, 2
 // have released it (empty).  No block barrier: a warp that is building does not stop the other three, and the build costs
 // each warp a quarter of a build per item instead of a whole one per two items in front of a barrier.
 constexpr int kTeamSlots = 4;
-constexpr int kClaimSlots = 64;
+constexpr int kClaimSlots = 1024;  // a CUDA graph keeps the slot it captured: two graphs replayed at the same time must not share one
 __device__ unsigned int g_roi_claim[kClaimSlots];
 
 struct TeamMeta {
@@ -1944,6 +1944,7 @@ __global__ void __launch_bounds__(512, 1)
   const uint64_t pol = l2_policy_evict_first();
   const int c0 = w * WI::kChannels;
   bool store_pending = false;
+  int exhausted = 0;
 #pragma unroll 1
   for (int i = -2;; ++i) {
     const int j = i + 2;
@@ -1972,7 +1973,17 @@ __global__ void __launch_bounds__(512, 1)
     const int s = i & 3;
     mbar_wait(&s_full[team][s], (uint32_t)((i >> 2) & 1));
     const TeamMeta m = s_meta[team][s];
-    if (m.k >= p.K) break;  // the list is exhausted (team-uniform: every warp reads the same header)
+    if (m.k >= p.K) {
+      // Past the end of the list.  The four builders claim concurrently, so the team's claims are not ordered ACROSS warps
+      // (RoI #i+1 may hold a smaller list index than RoI #i): one exhausted header does not end the team.  Each warp's own
+      // claims do increase, so four exhausted headers in a row (one from every builder) do.  (Team-uniform: every warp
+      // reads the same headers.)
+      if (++exhausted == kTeamSlots) break;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[team][s]);
+      continue;
+    }
+    exhausted = 0;
     const WarpTables<7>& tb = tbs[s];
     const LvParam& lv = p.lv[m.lvl];
     const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)m.b * lv.sn + c0 + 2 * lane);

@@ -973,6 +973,14 @@ __global__ void __launch_bounds__(128, ROWS == 2 ? 3 : 4)
   if (lane == 0) bulk_wait_read_all();
 }
 
+// A RoI that certainly has no row program (decided from its geometry alone, before any table is built): bins at least
+// 4.5 px wide put a bin's two samples (half a bin apart, two columns each) on five or more columns; a window over 34 px tall
+// spans more than 32 rows.  Only for RoIs that the map does not clip (a clipped one may still qualify: built and decided there).
+__device__ __forceinline__ bool row_program_hopeless(const RoiGeom& g, const LvParam& lv) {
+  return (g.bw >= 4.5f && g.sw >= 0.f && g.sw + 7.f * g.bw <= (float)lv.W - 1.f) ||
+         (g.bh * 7.f >= 34.f && g.sh >= 0.f && g.sh + 7.f * g.bh <= (float)lv.H - 1.f);
+}
+
 // ---- forward, row program with PIPELINED rows (P = 7, C == 256): LCR_ROI_FWD=rmp ---------------------------------
 // ncu of roi_fwd_warp_kernel / roi_fwd_rm_kernel on the bench list (profiles/r02b_*): 39-45 % of all warp samples are
 // long-scoreboard stalls, two thirds of them on the FIRST FMUL2 of a window row — a warp issues a row's 21-28 loads, has
@@ -1096,7 +1104,8 @@ __global__ void __launch_bounds__(128, 4)
     if (live) {
       const LvParam& lv = p.lv[g.lvl];
       run = build_tables_warp<7>(tbs[warp], g, lv, lane, 7);
-      if (run <= 4) nrows = build_row_program(tbs[warp], (uint32_t)lv.sh * 4u, lane, &span);
+      if (run <= 4 && !row_program_hopeless(g, lv)) nrows = build_row_program(tbs[warp], (uint32_t)lv.sh * 4u, lane, &span);
+      if (run == 4 && span > 1) nrows = -2;  // (rare: wide AND flat) bin-dense sample walk; its x taps now hold the row program
     }
     if (lane == 0) {
       s_run[warp] = run;
@@ -1117,13 +1126,13 @@ __global__ void __launch_bounds__(128, 4)
     const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)s_b[slot] * lv.sn + c0 + 2 * lane);
     const uint32_t swb = (uint32_t)lv.sw * 4u;
     const bool two = s_span[slot] <= 1;  // every window row feeds at most two bin rows (bins at least one pixel tall)
+    // (the folded x weights are re-read from shared memory per bin: held in registers next to the row's loaded columns they
+    // do not fit 128 registers — ptxas spilled them and the loop re-read them from local memory, 1.45 against 1.39 ms)
     if (nrows > 0 && run <= 3) {
-      if (two && !(flags & 4)) roi_warp_body_rmp<3, 2, CSW, true>(tb, nrows, fb, swb, my, store_pending);
-      else if (two) roi_warp_body_rmp<3, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending);
+      if (two) roi_warp_body_rmp<3, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending);
       else roi_warp_body_rmp<3, 3, CSW, false>(tb, nrows, fb, swb, my, store_pending);
     } else if (nrows > 0) {
-      if (two) roi_warp_body_rmp<4, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending);
-      else roi_warp_body_rmp<4, 3, CSW, false>(tb, nrows, fb, swb, my, store_pending);
+      roi_warp_body_rmp<4, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending);
     } else {
       if (store_pending) {
         if (lane == 0) bulk_wait_read_all();
@@ -1132,9 +1141,13 @@ __global__ void __launch_bounds__(128, 4)
       }
       if (run < 0 || nrows == 0) {  // padding row, or every sample outside the map
         for (int j = lane; j < WI::kTileFloats; j += 32) tile[j] = 0.f;
-      } else if (run <= 3) roi_warp_body<7, 7, 3, CSW>(tb, 0, fb, swb, my);
-      else if (run == 4) roi_warp_body<7, 7, 4, CSW>(tb, 0, fb, swb, my);
-      else roi_warp_body<7, 7, 0, CSW>(tb, 0, fb, swb, my);
+      } else {
+        // one sample-walk body for every RoI without a row program (per-sample taps: any geometry) — with the bin-dense
+        // NB = 3 / 4 walks inlined as well, a list mixing small and large RoIs ran 9 % slower than through
+        // roi_fwd_warp_kernel (instruction-cache misses: seven loop bodies side by side on an SM)
+        if (nrows == -2) roi_warp_body<7, 7, 4, CSW>(tb, 0, fb, swb, my);
+        else roi_warp_body<7, 7, 0, CSW>(tb, 0, fb, swb, my);
+      }
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -1912,9 +1925,94 @@ __global__ void __launch_bounds__((256 / WarpItem<7, XB>::kChannels + 2) * 32, 2
 // tables TWO RoIs ahead of where it pools, hands them over on an mbarrier (full), and reuses the slot when all four warps
 // have released it (empty).  No block barrier: a warp that is building does not stop the other three, and the build costs
 // each warp a quarter of a build per item instead of a whole one per two items in front of a barrier.
+// Marks a RoI the persistent kernel left to the second pass: an fp32 quiet-NaN bit pattern in the first word of the RoI's
+// output block.  The second pass recomputes every RoI whose first word holds it, so a genuine output that happened to carry
+// the same bits (a NaN with this payload) is merely pooled twice, with the same result.
+constexpr unsigned int kRestSentinel = 0x7fd5c3a9u;
+
+// Second pass of the two-pass forward: the RoIs the persistent kernel marked, through the sample-walk bodies of
+// roi_fwd_warp_kernel.  CTA b scans the first output words of RoIs [b*R, (b+1)*R) (one per thread), compacts the marked ones
+// and pools them four at a time (warp = 64-channel group, warp i builds the tables of the i-th RoI of the group).
+template <int CSW>
+__global__ void __launch_bounds__(128, 4)
+    roi_fwd_rest_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out, int flags, int R,
+                        const unsigned int* __restrict__ n_marked) {
+  if (__ldcg(n_marked) == 0u) return;  // nothing was left over: no scan (block-uniform)
+  using WI = WarpItem<7, 7>;
+  constexpr int WARPS = 4, PP = 49;
+  constexpr uint32_t kAll = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = __shfl_sync(kAll, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * WI::kTileFloats;
+  WarpTables<7>* tbs = reinterpret_cast<WarpTables<7>*>(smem_raw + sizeof(float) * WARPS * WI::kTileFloats);
+  __shared__ int s_run[WARPS], s_b[WARPS], s_lvl[WARPS];
+  __shared__ int s_cnt[WARPS + 1];
+  __shared__ int s_list[128];
+  const int k_mine = blockIdx.x * R + (int)threadIdx.x;
+  bool marked = false;
+  if ((int)threadIdx.x < R && k_mine < p.K)
+    marked = __ldcg(reinterpret_cast<const unsigned int*>(out + (size_t)k_mine * p.C * PP)) == kRestSentinel;
+  const uint32_t bal = __ballot_sync(kAll, marked);
+  if (lane == 0) s_cnt[warp + 1] = __popc(bal);
+  if (threadIdx.x == 0) s_cnt[0] = 0;
+  __syncthreads();
+  int before = 0;
+  for (int q = 0; q <= warp; ++q) before += s_cnt[q];
+  const int n = s_cnt[1] + s_cnt[2] + s_cnt[3] + s_cnt[4];
+  if (n == 0) return;  // block-uniform
+  if (marked) s_list[before + __popc(bal & ((1u << lane) - 1u))] = k_mine;
+  float* my = tile + (size_t)(2 * lane) * PP;
+  const uint64_t pol = l2_policy_evict_first();
+  const int c0 = warp * WI::kChannels;
+  constexpr int G = 2;  // RoIs per group
+  for (int g0 = 0; g0 < n; g0 += G) {
+    __syncthreads();  // the list is complete / the previous group's tables are no longer read
+    if (warp < G && g0 + warp < n) {
+      const RoiGeom g = roi_geom(p, s_list[g0 + warp]);
+      const bool live = __any_sync(kAll, g.live);
+      int run = -1;
+      if (live) run = build_tables_warp<7>(tbs[warp], g, p.lv[g.lvl], lane, 7);
+      if (lane == 0) {
+        s_run[warp] = run;
+        s_b[warp] = g.b;
+        s_lvl[warp] = live ? g.lvl : 0;
+      }
+    }
+    __syncthreads();
+    for (int slot = 0; slot < G && g0 + slot < n; ++slot) {
+      const int k = s_list[g0 + slot];
+      const int run = s_run[slot];
+      const WarpTables<7>& tb = tbs[slot];
+      const LvParam& lv = p.lv[s_lvl[slot]];
+      if (lane == 0) bulk_wait_read_all();  // the previous item's bulk store has finished reading the tile
+      __syncwarp();
+      if (run < 0) {
+        for (int q = lane; q < WI::kTileFloats; q += 32) tile[q] = 0.f;
+      } else {
+        const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)s_b[slot] * lv.sn + c0 + 2 * lane);
+        const uint32_t swb = (uint32_t)lv.sw * 4u;
+        if (run <= 3) roi_warp_body<7, 7, 3, CSW>(tb, 0, fb, swb, my);
+        else if (run == 4) roi_warp_body<7, 7, 4, CSW>(tb, 0, fb, swb, my);
+        else roi_warp_body<7, 7, 0, CSW>(tb, 0, fb, swb, my);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        float* dst = out + ((size_t)k * p.C + c0) * PP;
+        const uint32_t bytes = (uint32_t)(WI::kChannels * PP * sizeof(float));
+        if (flags & 1) bulk_store_smem_to_global_hint(dst, tile, bytes, pol);
+        else bulk_store_smem_to_global(dst, tile, bytes);
+        bulk_commit();
+      }
+    }
+  }
+  if (lane == 0) bulk_wait_read_all();
+}
+
 constexpr int kTeamSlots = 4;
 constexpr int kClaimSlots = 1024;  // a CUDA graph keeps the slot it captured: two graphs replayed at the same time must not share one
-__device__ unsigned int g_roi_claim[kClaimSlots];
+__device__ unsigned int g_roi_claim[kClaimSlots][2];  // [work counter, RoIs left to the second pass]
 
 struct TeamMeta {
   int k, run, b, lvl, nrows, span;
@@ -1961,8 +2059,12 @@ __global__ void __launch_bounds__(512, 1)
         if (live) {
           glvl = g.lvl;
           const LvParam& lv = p.lv[g.lvl];
-          run = build_tables_warp<7>(tbs[w], g, lv, lane, 7);
-          if (run <= 4) nrows = build_row_program(tbs[w], (uint32_t)lv.sh * 4u, lane, &span);
+          if (row_program_hopeless(g, lv)) {
+            run = 99;  // no tables: the second pass builds its own
+          } else {
+            run = build_tables_warp<7>(tbs[w], g, lv, lane, 7);
+            if (run <= 4) nrows = build_row_program(tbs[w], (uint32_t)lv.sh * 4u, lane, &span);
+          }
         }
       }
       if (lane == 0) s_meta[team][w] = TeamMeta{k, run, gb, glvl, nrows, span};
@@ -1988,25 +2090,35 @@ __global__ void __launch_bounds__(512, 1)
     const LvParam& lv = p.lv[m.lvl];
     const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)m.b * lv.sn + c0 + 2 * lane);
     const uint32_t swb = (uint32_t)lv.sw * 4u;
-    const bool two = m.span <= 1;
-    if (m.nrows > 0 && m.run <= 3) {
-      if (two && (flags & 4)) roi_warp_body_rmp<3, 2, CSW, true>(tb, m.nrows, fb, swb, my, store_pending);
-      else if (two) roi_warp_body_rmp<3, 2, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
-      else roi_warp_body_rmp<3, 3, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
-    } else if (m.nrows > 0) {
-      if (two) roi_warp_body_rmp<4, 2, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
-      else roi_warp_body_rmp<4, 3, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
-    } else {
+    // Row-program RoIs only.  16 warps of one CTA run their bodies side by side: with the sample-walk bodies inlined here
+    // too, a list that mixes small and large RoIs spent 56 % of its warp samples waiting for instructions (ncu
+    // stall_no_inst; 0.75 ms against 0.46 ms for the same list sorted by size).  A RoI without a row program (bins wider
+    // than four columns, windows taller than 32 rows, bins under ~0.7 px) is LEFT to the second pass
+    // (roi_fwd_rest_kernel): the first word of its output block receives kRestSentinel.
+    const bool two = m.span <= 1;  // every window row feeds at most two bin rows
+    if (m.nrows > 0 && m.run <= 3 && two) {
+      roi_warp_body_rmp<3, 2, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
+    } else if (m.nrows > 0 && m.run <= 3) {
+      roi_warp_body_rmp<3, 3, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
+    } else if (m.nrows > 0 && two) {
+      roi_warp_body_rmp<4, 2, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
+    } else if (m.run < 0 || m.nrows == 0) {  // padding row, or every sample outside the map: zeros
       if (store_pending) {
         if (lane == 0) bulk_wait_read_all();
         __syncwarp();
         store_pending = false;
       }
-      if (m.run < 0 || m.nrows == 0) {  // padding row, or every sample outside the map
-        for (int q = lane; q < WI::kTileFloats; q += 32) tile[q] = 0.f;
-      } else if (m.run <= 3) roi_warp_body<7, 7, 3, CSW>(tb, 0, fb, swb, my);
-      else if (m.run == 4) roi_warp_body<7, 7, 4, CSW>(tb, 0, fb, swb, my);
-      else roi_warp_body<7, 7, 0, CSW>(tb, 0, fb, swb, my);
+      for (int q = lane; q < WI::kTileFloats; q += 32) tile[q] = 0.f;
+    } else {
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[team][s]);
+        if (w == 0) {
+          *reinterpret_cast<unsigned int*>(out + (size_t)m.k * p.C * PP) = kRestSentinel;
+          atomicAdd(claim + 1, 1u);
+        }
+      }
+      continue;
     }
     fence_proxy_async_smem();
     __syncwarp();  // the tile is complete and every lane is done with the table slot
@@ -2261,8 +2373,7 @@ static int launch_fwd_rmp(const RoiParams& p, float* out, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e);
     configured_dev = dev;
   }
-  // flags: bit 0 = evict-first output stores, bit 2 = folded x weights re-read from shared memory instead of held in registers
-  const int flags = (tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (tune_is("LCR_ROI_XW", "smem") ? 4 : 0);
+  const int flags = tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1;  // bit 0 = evict-first output stores
   kern<<<(unsigned)want, WARPS * 32, smem, st>>>(p, out, flags, ipw);
   return after_launch();
 }
@@ -2285,14 +2396,31 @@ static int launch_fwd_team_impl(const RoiParams& p, float* out, cudaStream_t st,
     configured_dev = dev;
   }
   // one work counter per launch (launches in flight at the same time on different streams must not share one)
-  unsigned int* claim = claim_base + (next_claim.fetch_add(1, std::memory_order_relaxed) % kClaimSlots);
-  cudaError_t e = cudaMemsetAsync(claim, 0, sizeof(unsigned int), st);
+  unsigned int* claim = claim_base + 2 * (next_claim.fetch_add(1, std::memory_order_relaxed) % kClaimSlots);
+  cudaError_t e = cudaMemsetAsync(claim, 0, 2 * sizeof(unsigned int), st);
   if (e != cudaSuccess) return cuda_status(e);
-  // flags: bit 0 = evict-first output stores, bit 2 = folded x weights held in registers (NB = 3, two accumulator sets)
-  const int flags = (tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1) | (tune_is("LCR_ROI_XW", "reg") ? 4 : 0);
+  const int flags = tune_is("LCR_ROI_STREAM_OUT", "0") ? 0 : 1;  // bit 0 = evict-first output stores
   const int grid = sm_count();
   if (csw256) roi_fwd_team_kernel<256><<<grid, WARPS * 32, smem, st>>>(p, out, flags, claim);
   else roi_fwd_team_kernel<0><<<grid, WARPS * 32, smem, st>>>(p, out, flags, claim);
+  int rc = after_launch();
+  if (rc != LCR_OK || tune_is("LCR_ROI_TEAM_PASS2", "0")) return rc;  // ("0": A/B timing of the first pass alone)
+  // second pass: the RoIs the first left marked.  R RoIs per CTA: few enough CTAs that an all-row-program list costs one
+  // short wave of scans, enough of them that a list of large RoIs still fills the GPU.
+  constexpr int RW = 4;
+  const size_t smem2 = sizeof(float) * RW * WI::kTileFloats + RW * sizeof(WarpTables<7>);
+  static thread_local int configured2 = -1;
+  if (configured2 != dev) {
+    cudaError_t e2 = cudaFuncSetAttribute(roi_fwd_rest_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(roi_fwd_rest_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e2 != cudaSuccess) return cuda_status(e2);
+    configured2 = dev;
+  }
+  int R = (p.K + 4 * 4 * grid - 1) / (4 * 4 * grid);
+  R = R < 4 ? 4 : (R > 128 ? 128 : (R + 3) / 4 * 4);
+  const int blocks = (p.K + R - 1) / R;
+  if (csw256) roi_fwd_rest_kernel<256><<<blocks, RW * 32, smem2, st>>>(p, out, flags & 1, R, claim + 1);
+  else roi_fwd_rest_kernel<0><<<blocks, RW * 32, smem2, st>>>(p, out, flags & 1, R, claim + 1);
   return after_launch();
 }
 }  // namespace lcr
@@ -2325,6 +2453,12 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
       if (all_sw_equal(p, 256)) return two ? launch_fwd_rm<2, 256>(p, out, st) : launch_fwd_rm<1, 256>(p, out, st);
       return two ? launch_fwd_rm<2, 0>(p, out, st) : launch_fwd_rm<1, 0>(p, out, st);
     }
+    // Default for the reference's pooler shape (7x7, 256 channels): the launch-ordered row-program kernel with pipelined rows
+    // (bench list 1.40 against 1.47 ms for roi_fwd_warp_kernel, and +2 % on the streamed step, where the persistent team
+    // kernel — 1.29 ms on its own — loses the overlap with the paste kernel because its CTAs hold the SM's whole shared
+    // memory from start to end).  LCR_ROI_FWD=warp selects the sample-walk kernel.
+    if (rm_eligible(p) && !tune_get("LCR_ROI_FWD"))
+      return all_sw_equal(p, 256) ? launch_fwd_rmp<256>(p, out, st) : launch_fwd_rmp<0>(p, out, st);
     if (warp_eligible(p) && !tune_is("LCR_ROI_FWD", "cta")) {
       // (P = 7 with 32-channel items — half-warps taking x-bins 0-3 / 4-6, XB = 4, 6 CTAs/SM instead of 4 — was measured
       // 10 % slower than the 64-channel items on B200: the extra occupancy does not pay for the 8-slots-for-7-bins padding.)

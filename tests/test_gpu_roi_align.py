@@ -187,7 +187,7 @@ def test_staged_forward_is_bit_identical_to_the_warp_kernel(ops, synth, oracle, 
         lv = oracle.level_map(rois[:, 1:], 2, 1 + levels, 224.0, 4).astype(np.int32)
     fd = [nhwc(T(f)) for f in feats]
     lvd = None if lv is None else T(lv)
-    tune(LCR_ROI_FWD=None)                                           # default dispatch: the warp kernel
+    tune(LCR_ROI_FWD="warp")                                         # the sample-walk warp kernel
     ref = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
     tune(LCR_ROI_FWD="staged")
     got = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
@@ -272,7 +272,7 @@ def test_abi_rejects_non_dense_zero_fill_and_ignores_bad_levels(ops, synth):
     assert torch.allclose(gin, gref, rtol=0, atol=1e-5)
 
 
-@pytest.mark.parametrize("variant", ["rm", "rm1", "rmp", "rmp_xwsmem", "team", "team_xwreg"])
+@pytest.mark.parametrize("variant", ["rm", "rm1", "rmp", "team", None])
 @pytest.mark.parametrize("K,mode,levels", [(600, "anchor", 1), (41, "anchor", 1), (2500, "fpn", 4)])
 def test_row_major_forward(ops, synth, oracle, tune, variant, K, mode, levels):
     """roi_fwd_rm_kernel (row program: distinct window rows with pre-added y weights into three rotating accumulator sets;
@@ -293,14 +293,9 @@ def test_row_major_forward(ops, synth, oracle, tune, variant, K, mode, levels):
     lv = None if levels == 1 else oracle.level_map(rois[:, 1:], 2, 1 + levels, 224.0, 4).astype(np.int32)
     fd = [nhwc(T(f)) for f in feats]
     lvd = None if lv is None else T(lv)
-    tune(LCR_ROI_FWD=None)
+    tune(LCR_ROI_FWD="warp")
     ref = N(ops.roi_align_fwd(fd, scales, T(rois), lvd, (7, 7), 2, False))
-    if variant == "rmp_xwsmem":
-        tune(LCR_ROI_FWD="rmp", LCR_ROI_XW="smem")
-    elif variant == "team_xwreg":
-        tune(LCR_ROI_FWD="team", LCR_ROI_XW="reg")
-    else:
-        tune(LCR_ROI_FWD=variant)
+    tune(LCR_ROI_FWD=variant)
     # into a NaN-filled buffer: a RoI the kernel skips must not pass on whatever the allocator left there (the persistent
     # team kernel once ended a team at its first exhausted claim and left RoIs claimed out of order unwritten)
     canvas = torch.full((K, C, 7, 7), float("nan"), device="cuda:0")

@@ -68,7 +68,7 @@ def main():
         print(json.dumps(kw), flush=True)
 
     def setenv(env):
-        for k in ("LCR_ROI_XW", "LCR_ROI_RING_KB", "LCR_ROI_STAGED_WARPS", "LCR_ROI_RPC", "LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_PASTE_CTAS", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
+        for k in ("LCR_ROI_TEAM_PASS2", "LCR_ROI_XW", "LCR_ROI_RING_KB", "LCR_ROI_STAGED_WARPS", "LCR_ROI_RPC", "LCR_ROI_FWD", "LCR_ROI_STREAM_OUT", "LCR_PASTE", "LCR_ROI_BWD", "LCR_ROI_IPW", "LCR_SELECT", "LCR_ROI_SPLIT", "LCR_PASTE_ZB_KB", "LCR_PASTE_CTAS", "LCR_ROI_SHARED_TABLES", "LCR_NMS_SPAN",
                   "LCR_NMS_RESOLVE"):
             _lib.set_tuning(k, None)       # the library reads the environment only once: switches go through lcr_set_tuning
         for k, v in env.items():
@@ -78,11 +78,11 @@ def main():
         bytes_roi = 4 * n_props * B.C * 49 + F * 4 * B.C * B.FH * B.FW + 20 * F * B.POST_NMS
         ref = None
         S = {"LCR_ROI_FWD": "staged"}
-        for name, env in [("warp,ipw2 (default)", {}),
+        for name, env in [("sample walk (warp), ipw2", {"LCR_ROI_FWD": "warp"}),
+                          ("default", {}),
                           ("persistent teams (team)", {"LCR_ROI_FWD": "team"}),
-                          ("persistent teams, x weights in registers", {"LCR_ROI_FWD": "team", "LCR_ROI_XW": "reg"}),
+                          ("persistent teams, first pass only", {"LCR_ROI_FWD": "team", "LCR_ROI_TEAM_PASS2": "0"}),
                           ("row program, pipelined rows (rmp)", {"LCR_ROI_FWD": "rmp"}),
-                          ("rmp, x weights from shared memory", {"LCR_ROI_FWD": "rmp", "LCR_ROI_XW": "smem"}),
                           ("rmp, ipw1", {"LCR_ROI_FWD": "rmp", "LCR_ROI_IPW": "1"}),
                           ("rmp, ipw3", {"LCR_ROI_FWD": "rmp", "LCR_ROI_IPW": "3"}),
                           ("rmp, ipw4", {"LCR_ROI_FWD": "rmp", "LCR_ROI_IPW": "4"}),
@@ -95,7 +95,7 @@ def main():
                           ("staged: 4 pooling warps, ring 56 KB", {**S, "LCR_ROI_STAGED_WARPS": "4"}),
                           ("staged: 4 warps, ring 150 KB (1 CTA/SM), rpc 32", {**S, "LCR_ROI_RING_KB": "150", "LCR_ROI_RPC": "32", "LCR_ROI_STAGED_WARPS": "4"}),
                           ("staged kernel, nothing staged (consumers gather)", {"LCR_ROI_FWD": "staged_direct"}),
-                          ("warp,ipw2 (again)", {})]:
+                          ("sample walk (warp) again", {"LCR_ROI_FWD": "warp"})]:
             setenv(env)
             out = pipe.pool(feat, props.rois)
             torch.cuda.synchronize()

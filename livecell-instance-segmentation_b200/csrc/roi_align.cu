@@ -981,6 +981,21 @@ __device__ __forceinline__ bool row_program_hopeless(const RoiGeom& g, const LvP
          (g.bh * 7.f >= 34.f && g.sh >= 0.f && g.sh + 7.f * g.bh <= (float)lv.H - 1.f);
 }
 
+// The y half of build_tables_warp (what build_row_program reads), for a warp that builds a RoI's row program while another
+// warp builds the RoI's x tables.
+__device__ __forceinline__ void build_y_taps(WarpTables<7>& tb, const RoiGeom& g, const LvParam& lv, int lane) {
+  __syncwarp();
+  if (lane < 14) {
+    int lo, hi;
+    float wl, wh;
+    const bool ok = axis_tap(sample_pos(g.sh, lane >> 1, g.bh, lane & 1, 2, g.cpu_coords), lv.H, lo, hi, wl, wh);
+    tb.ys[lane] = AxisTapB{(uint32_t)(lo * lv.sh) * 4u, (uint32_t)(hi * lv.sh) * 4u, wl, wh};
+    tb.lo[1][lane] = ok ? lo : -1;
+    tb.hi[1][lane] = hi;
+  }
+  __syncwarp();
+}
+
 // ---- forward, row program with PIPELINED rows (P = 7, C == 256): LCR_ROI_FWD=rmp ---------------------------------
 // ncu of roi_fwd_warp_kernel / roi_fwd_rm_kernel on the bench list (profiles/r02b_*): 39-45 % of all warp samples are
 // long-scoreboard stalls, two thirds of them on the FIRST FMUL2 of a window row — a warp issues a row's 21-28 loads, has
@@ -992,10 +1007,10 @@ __device__ __forceinline__ bool row_program_hopeless(const RoiGeom& g, const LvP
 // the top of the item to the first tile write.
 template <int NB, int NACC, int CSW, bool XWREG>
 __device__ __forceinline__ void roi_warp_body_rmp(const WarpTables<7>& tb, int nrows, const char* __restrict__ fb, uint32_t swb,
-                                                  float* __restrict__ my, bool& store_pending) {
+                                                  float* __restrict__ my, bool& store_pending, const RowOp* rows_at = nullptr) {
   constexpr int P = 7, PP = 49;
   const uint32_t cs = CSW ? (uint32_t)CSW * 4u : swb;
-  const RowOp* rows = reinterpret_cast<const RowOp*>(tb.xs);
+  const RowOp* rows = rows_at ? rows_at : reinterpret_cast<const RowOp*>(tb.xs);  // (where build_row_program left it)
   uint32_t xo[P];
   float2 acc0[P], acc1[P], acc2[P];
   float xwr[P][XWREG ? NB : 1];
@@ -1096,23 +1111,37 @@ __global__ void __launch_bounds__(128, 4)
   __shared__ int s_run[WARPS], s_b[WARPS], s_lvl[WARPS], s_rows[WARPS], s_span[WARPS];
   float* my = tile + (size_t)(2 * lane) * PP;
   const uint64_t pol = l2_policy_evict_first();
+  // Table build, split over the CTA's four warps (ipw <= 2 RoIs per CTA): warp i builds RoI i's x / y tap tables and folded
+  // bin weights in slot i, warp 2 + i builds RoI i's row program (from its own copy of the y taps) in slot 2 + i — the two
+  // halves of what was one warp's dependent chain in front of the barrier (7.6 % of the warp samples waited there).
   const int k0 = blockIdx.x * ipw;
-  if (warp < ipw && k0 + warp < p.K) {
-    const RoiGeom g = roi_geom(p, k0 + warp);
-    const bool live = __any_sync(kAll, g.live);
-    int run = -1, nrows = -1, span = 2;
-    if (live) {
-      const LvParam& lv = p.lv[g.lvl];
-      run = build_tables_warp<7>(tbs[warp], g, lv, lane, 7);
-      if (run <= 4 && !row_program_hopeless(g, lv)) nrows = build_row_program(tbs[warp], (uint32_t)lv.sh * 4u, lane, &span);
-      if (run == 4 && span > 1) nrows = -2;  // (rare: wide AND flat) bin-dense sample walk; its x taps now hold the row program
-    }
-    if (lane == 0) {
-      s_run[warp] = run;
-      s_b[warp] = g.b;
-      s_lvl[warp] = live ? g.lvl : 0;
-      s_rows[warp] = nrows;
-      s_span[warp] = span;
+  {
+    const int r = warp & 1;  // RoI of this warp
+    if (r < ipw && k0 + r < p.K) {
+      const RoiGeom g = roi_geom(p, k0 + r);
+      const bool live = __any_sync(kAll, g.live);
+      if (warp < 2) {
+        int run = -1;
+        if (live) run = build_tables_warp<7>(tbs[r], g, p.lv[g.lvl], lane, 7);
+        if (lane == 0) {
+          s_run[r] = run;
+          s_b[r] = g.b;
+          s_lvl[r] = live ? g.lvl : 0;
+        }
+      } else {
+        int nrows = -1, span = 2;
+        if (live) {
+          const LvParam& lv = p.lv[g.lvl];
+          if (!row_program_hopeless(g, lv)) {
+            build_y_taps(tbs[2 + r], g, lv, lane);
+            nrows = build_row_program(tbs[2 + r], (uint32_t)lv.sh * 4u, lane, &span);
+          }
+        }
+        if (lane == 0) {
+          s_rows[r] = nrows;
+          s_span[r] = span;
+        }
+      }
     }
   }
   __syncthreads();
@@ -1126,13 +1155,14 @@ __global__ void __launch_bounds__(128, 4)
     const char* fb = reinterpret_cast<const char*>(lv.data + (size_t)s_b[slot] * lv.sn + c0 + 2 * lane);
     const uint32_t swb = (uint32_t)lv.sw * 4u;
     const bool two = s_span[slot] <= 1;  // every window row feeds at most two bin rows (bins at least one pixel tall)
+    const RowOp* rows = reinterpret_cast<const RowOp*>(tbs[2 + slot].xs);
     // (the folded x weights are re-read from shared memory per bin: held in registers next to the row's loaded columns they
     // do not fit 128 registers — ptxas spilled them and the loop re-read them from local memory, 1.45 against 1.39 ms)
-    if (nrows > 0 && run <= 3) {
-      if (two) roi_warp_body_rmp<3, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending);
-      else roi_warp_body_rmp<3, 3, CSW, false>(tb, nrows, fb, swb, my, store_pending);
-    } else if (nrows > 0) {
-      roi_warp_body_rmp<4, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending);
+    if (nrows > 0 && run >= 0 && run <= 3) {
+      if (two) roi_warp_body_rmp<3, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending, rows);
+      else roi_warp_body_rmp<3, 3, CSW, false>(tb, nrows, fb, swb, my, store_pending, rows);
+    } else if (nrows > 0 && run == 4 && two) {
+      roi_warp_body_rmp<4, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending, rows);
     } else {
       if (store_pending) {
         if (lane == 0) bulk_wait_read_all();
@@ -1145,8 +1175,7 @@ __global__ void __launch_bounds__(128, 4)
         // one sample-walk body for every RoI without a row program (per-sample taps: any geometry) — with the bin-dense
         // NB = 3 / 4 walks inlined as well, a list mixing small and large RoIs ran 9 % slower than through
         // roi_fwd_warp_kernel (instruction-cache misses: seven loop bodies side by side on an SM)
-        if (nrows == -2) roi_warp_body<7, 7, 4, CSW>(tb, 0, fb, swb, my);
-        else roi_warp_body<7, 7, 0, CSW>(tb, 0, fb, swb, my);
+        roi_warp_body<7, 7, 0, CSW>(tb, 0, fb, swb, my);
       }
     }
     fence_proxy_async_smem();
@@ -2360,8 +2389,8 @@ static int launch_fwd_rmp(const RoiParams& p, float* out, cudaStream_t st) {
   using WI = WarpItem<7, 7>;
   constexpr int WARPS = 4;
   const size_t smem = sizeof(float) * WARPS * WI::kTileFloats + WARPS * sizeof(WarpTables<7>);
-  int ipw = p.K >= 2 * 4 * sm_count() ? 2 : 1;
-  if (const char* v = tune_get("LCR_ROI_IPW")) ipw = atoi(v) >= 1 && atoi(v) <= WARPS ? atoi(v) : ipw;
+  int ipw = p.K >= 2 * 4 * sm_count() ? 2 : 1;  // RoIs per CTA (1 or 2: two table slots + two row-program slots)
+  if (const char* v = tune_get("LCR_ROI_IPW")) ipw = atoi(v) == 1 ? 1 : (atoi(v) == 2 ? 2 : ipw);
   const long long want = ((long long)p.K + ipw - 1) / ipw;
   LCR_REQUIRE(want < (1ll << 31), LCR_ERR_CAPACITY);
   auto kern = roi_fwd_rmp_kernel<CSW>;

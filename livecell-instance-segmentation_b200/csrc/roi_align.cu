@@ -1067,7 +1067,7 @@ __device__ __forceinline__ void roi_warp_body_rmp(const WarpTables<7>& tb, int n
 #pragma unroll 1
   for (int i = 0; i < nrows; ++i) {
     const bool more = i + 1 < nrows;  // warp-uniform
-    const RowOp op = rows[i];
+    const RowOp op = rows[i];  // (read one row ahead it costs four registers: ptxas spills in the loop, 1.33 -> 1.43 ms)
     const char* nrow = fb + (rows[more ? i + 1 : i].off_pa & ~7u);
     retire((int)(op.off_pa & 7u));
     const float2 w0 = splat(op.w0), w1 = splat(op.w1), w2 = splat(op.w2);
@@ -1111,6 +1111,7 @@ __global__ void __launch_bounds__(128, 4)
   __shared__ int s_run[WARPS], s_b[WARPS], s_lvl[WARPS], s_rows[WARPS], s_span[WARPS];
   float* my = tile + (size_t)(2 * lane) * PP;
   const uint64_t pol = l2_policy_evict_first();
+  // (an L2 prefetch of the RoI rows of the CTA two waves further down changed nothing: 1.331 ms either way)
   // Table build, split over the CTA's four warps (ipw <= 2 RoIs per CTA): warp i builds RoI i's x / y tap tables and folded
   // bin weights in slot i, warp 2 + i builds RoI i's row program (from its own copy of the y taps) in slot 2 + i — the two
   // halves of what was one warp's dependent chain in front of the barrier (7.6 % of the warp samples waited there).
@@ -2486,7 +2487,9 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
     // (bench list 1.40 against 1.47 ms for roi_fwd_warp_kernel, and +2 % on the streamed step, where the persistent team
     // kernel — 1.29 ms on its own — loses the overlap with the paste kernel because its CTAs hold the SM's whole shared
     // memory from start to end).  LCR_ROI_FWD=warp selects the sample-walk kernel.
-    if (rm_eligible(p) && !tune_get("LCR_ROI_FWD"))
+    // Lists that fill the GPU with two-RoI CTAs only: below that the kernel is latency-bound per CTA and the shorter table
+    // build of the sample-walk kernel wins by 2-3 us (C3: one frame, 896 RoIs).
+    if (rm_eligible(p) && !tune_get("LCR_ROI_FWD") && K >= 2 * 4 * sm_count())
       return all_sw_equal(p, 256) ? launch_fwd_rmp<256>(p, out, st) : launch_fwd_rmp<0>(p, out, st);
     if (warp_eligible(p) && !tune_is("LCR_ROI_FWD", "cta")) {
       // (P = 7 with 32-channel items — half-warps taking x-bins 0-3 / 4-6, XB = 4, 6 CTAs/SM instead of 4 — was measured

@@ -15,8 +15,8 @@ done
 # parametrised RoIAlign tests); the switches also work from the environment (read once at library load):
 LCR_SELECT=general LCR_NMS_RESOLVE=serial timeout 600 python -m pytest tests/test_gpu_select.py tests/test_gpu_nms.py tests/test_gpu_pipeline.py -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/test_env_select_nms.log 2>&1
 rc=$?; echo "env switches (general select, serial NMS resolve) rc=$rc: $(tail -1 gpurun_out/test_env_select_nms.log)"; [ $rc -ne 0 ] && status=1
-LCR_ROI_FWD=staged LCR_PASTE=single LCR_TORCH_EXT=0 timeout 600 python -m pytest tests/test_gpu_roi_align.py tests/test_gpu_paste.py tests/test_gpu_pipeline.py tests/test_gpu_fuzz.py -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/test_env_roi_paste.log 2>&1
-rc=$?; echo "env switches (staged RoIAlign, single-role paste, ctypes call path) rc=$rc: $(tail -1 gpurun_out/test_env_roi_paste.log)"; [ $rc -ne 0 ] && status=1
+LCR_ROI_FWD=warp LCR_PASTE=single LCR_TORCH_EXT=0 timeout 600 python -m pytest tests/test_gpu_roi_align.py tests/test_gpu_paste.py tests/test_gpu_pipeline.py tests/test_gpu_fuzz.py -m gpu -q -x --tb=short -p no:cacheprovider > gpurun_out/test_env_roi_paste.log 2>&1
+rc=$?; echo "env switches (sample-walk RoIAlign, single-role paste, ctypes call path) rc=$rc: $(tail -1 gpurun_out/test_env_roi_paste.log)"; [ $rc -ne 0 ] && status=1
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 rc=$?; echo "smoke rc=$rc: $(tail -1 gpurun_out/smoke.log)"; [ $rc -ne 0 ] && status=1
 if [ "$1" != "--no-bench" ]; then

@@ -1005,7 +1005,7 @@ __device__ __forceinline__ void build_y_taps(WarpTables<7>& tb, const RoiGeom& g
 // flight during this row's remaining FMAs, the accumulator rotation and the tile stores, and a warp's wait per row shrinks
 // from (round trip) to (round trip - row compute).  The wait for the previous item's bulk store (tile reuse) moves from
 // the top of the item to the first tile write.
-template <int NB, int NACC, int CSW, bool XWREG>
+template <int NB, int NACC, int CSW, int XWR>
 __device__ __forceinline__ void roi_warp_body_rmp(const WarpTables<7>& tb, int nrows, const char* __restrict__ fb, uint32_t swb,
                                                   float* __restrict__ my, bool& store_pending, const RowOp* rows_at = nullptr) {
   constexpr int P = 7, PP = 49;
@@ -1013,19 +1013,21 @@ __device__ __forceinline__ void roi_warp_body_rmp(const WarpTables<7>& tb, int n
   const RowOp* rows = rows_at ? rows_at : reinterpret_cast<const RowOp*>(tb.xs);  // (where build_row_program left it)
   uint32_t xo[P];
   float2 acc0[P], acc1[P], acc2[P];
-  float xwr[P][XWREG ? NB : 1];
+  float xwr[XWR > 0 ? XWR : 1][NB];  // the folded x weights of bins 0 .. XWR-1 (the rest are re-read from shared memory per row)
 #pragma unroll
   for (int pw = 0; pw < P; ++pw) {
     xo[pw] = tb.xoff[pw];
     acc0[pw] = acc1[pw] = acc2[pw] = make_float2(0.f, 0.f);
-    if (XWREG) {
+    if (pw < XWR) {
       const float4 w = tb.xw[pw];
-      xwr[pw][0] = w.x;
-      if (NB > 1) xwr[pw][1 % NB] = w.y;
-      if (NB > 2) xwr[pw][2 % NB] = w.z;
-      if (NB > 3) xwr[pw][3 % NB] = w.w;
+      xwr[pw % (XWR > 0 ? XWR : 1)][0] = w.x;
+      if (NB > 1) xwr[pw % (XWR > 0 ? XWR : 1)][1 % NB] = w.y;
+      if (NB > 2) xwr[pw % (XWR > 0 ? XWR : 1)][2 % NB] = w.z;
+      if (NB > 3) xwr[pw % (XWR > 0 ? XWR : 1)][3 % NB] = w.w;
     }
   }
+  // (Not loading a bin's LAST column when it carries no weight — both samples on the first NB-1 columns, 20-60 % of the bins —
+  // was tried for the LSU wavefronts it saves: the per-bin predicate costs registers the body does not have, 1.33 -> 1.37 ms.)
   const bool lower = (threadIdx.x & 16) == 0;  // conflict-free tile stores, see roi_warp_body
   float* const o_a = my + (lower ? 0 : PP);
   float* const o_b = my + (lower ? PP : 0);
@@ -1074,9 +1076,9 @@ __device__ __forceinline__ void roi_warp_body_rmp(const WarpTables<7>& tb, int n
 #pragma unroll
     for (int pw = 0; pw < P; ++pw) {
       float xw[4];
-      if (XWREG) {
+      if (pw < XWR) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) xw[j] = xwr[pw][j];
+        for (int j = 0; j < NB; ++j) xw[j] = xwr[pw % (XWR > 0 ? XWR : 1)][j];
       } else {
         const float4 xw4 = tb.xw[pw];
         xw[0] = xw4.x; xw[1] = xw4.y; xw[2] = xw4.z; xw[3] = xw4.w;
@@ -1157,13 +1159,14 @@ __global__ void __launch_bounds__(128, 4)
     const uint32_t swb = (uint32_t)lv.sw * 4u;
     const bool two = s_span[slot] <= 1;  // every window row feeds at most two bin rows (bins at least one pixel tall)
     const RowOp* rows = reinterpret_cast<const RowOp*>(tbs[2 + slot].xs);
-    // (the folded x weights are re-read from shared memory per bin: held in registers next to the row's loaded columns they
-    // do not fit 128 registers — ptxas spilled them and the loop re-read them from local memory, 1.45 against 1.39 ms)
+    // (XWR = 0: the folded x weights are re-read from shared memory per bin and row — 7 of a row's ~51 LSU wavefronts, on the
+    // unit that bounds the kernel.  The bodies sit exactly at 128 registers: holding even three bins' weights in registers
+    // makes ptxas spill inside the row loop (XWR = 7: 1.45 against 1.39 ms; XWR = 3: 16 bytes spilled).)
     if (nrows > 0 && run >= 0 && run <= 3) {
-      if (two) roi_warp_body_rmp<3, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending, rows);
-      else roi_warp_body_rmp<3, 3, CSW, false>(tb, nrows, fb, swb, my, store_pending, rows);
+      if (two) roi_warp_body_rmp<3, 2, CSW, 0>(tb, nrows, fb, swb, my, store_pending, rows);
+      else roi_warp_body_rmp<3, 3, CSW, 0>(tb, nrows, fb, swb, my, store_pending, rows);
     } else if (nrows > 0 && run == 4 && two) {
-      roi_warp_body_rmp<4, 2, CSW, false>(tb, nrows, fb, swb, my, store_pending, rows);
+      roi_warp_body_rmp<4, 2, CSW, 0>(tb, nrows, fb, swb, my, store_pending, rows);
     } else {
       if (store_pending) {
         if (lane == 0) bulk_wait_read_all();
@@ -2127,11 +2130,11 @@ __global__ void __launch_bounds__(512, 1)
     // (roi_fwd_rest_kernel): the first word of its output block receives kRestSentinel.
     const bool two = m.span <= 1;  // every window row feeds at most two bin rows
     if (m.nrows > 0 && m.run <= 3 && two) {
-      roi_warp_body_rmp<3, 2, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
+      roi_warp_body_rmp<3, 2, CSW, 0>(tb, m.nrows, fb, swb, my, store_pending);
     } else if (m.nrows > 0 && m.run <= 3) {
-      roi_warp_body_rmp<3, 3, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
+      roi_warp_body_rmp<3, 3, CSW, 0>(tb, m.nrows, fb, swb, my, store_pending);
     } else if (m.nrows > 0 && two) {
-      roi_warp_body_rmp<4, 2, CSW, false>(tb, m.nrows, fb, swb, my, store_pending);
+      roi_warp_body_rmp<4, 2, CSW, 0>(tb, m.nrows, fb, swb, my, store_pending);
     } else if (m.run < 0 || m.nrows == 0) {  // padding row, or every sample outside the map: zeros
       if (store_pending) {
         if (lane == 0) bulk_wait_read_all();

@@ -200,7 +200,7 @@ int lcr_level_map_f32(const float* boxes, int box_stride, int K, int k_min, int 
  * and, with L > 1 and roi_level given, MultiScaleRoIAlign (TV:ops/poolers.py:147-227).
  *
  * Each level is a [N, C, H, W] fp32 tensor addressed through ELEMENT strides, so both NCHW and
- * channels_last (NHWC memory) maps are accepted.  Forward dispatch on the fast path: PH == PW == 7, C == 256 and K >= 8 x SMs (the
+ * channels_last (NHWC memory) maps are accepted.  Forward dispatch on the fast path: PH == PW == 7, C == 256, K >= 8 x SMs and N >= 4 frames (the
  * reference's pooler on a serving batch) runs the row-program kernel with pipelined rows (roi_fwd_rmp_kernel: results within ~1e-7 of the
  * sample-walk kernel, the taps of a shared window row are pre-added); everything else the sample-walk warp kernel.  A persistent variant
  * (LCR_ROI_FWD=team) uses two words of library-owned device memory per launch (a work counter; 1024 rotating slots, so launches that

@@ -2490,9 +2490,11 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
     // (bench list 1.40 against 1.47 ms for roi_fwd_warp_kernel, and +2 % on the streamed step, where the persistent team
     // kernel — 1.29 ms on its own — loses the overlap with the paste kernel because its CTAs hold the SM's whole shared
     // memory from start to end).  LCR_ROI_FWD=warp selects the sample-walk kernel.
-    // Lists that fill the GPU with two-RoI CTAs only: below that the kernel is latency-bound per CTA and the shorter table
-    // build of the sample-walk kernel wins by 2-3 us (C3: one frame, 896 RoIs).
-    if (rm_eligible(p) && !tune_get("LCR_ROI_FWD") && K >= 2 * 4 * sm_count())
+    // Serving batches only: lists that fill the GPU with two-RoI CTAs (below that the kernel is latency-bound per CTA and the
+    // shorter table build of the sample-walk kernel wins by 2-3 us — C3: one frame, 896 RoIs) over at least four frames (the
+    // single-map sweeps of BASELINE config C5 mix in RoIs of 30-45 feature px, which take this kernel's one sample-walk body:
+    // 2-5 % slower there than roi_fwd_warp_kernel, profiles/r02b_roi_ksweep.jsonl).
+    if (rm_eligible(p) && !tune_get("LCR_ROI_FWD") && K >= 2 * 4 * sm_count() && p.lv[0].N >= 4)
       return all_sw_equal(p, 256) ? launch_fwd_rmp<256>(p, out, st) : launch_fwd_rmp<0>(p, out, st);
     if (warp_eligible(p) && !tune_is("LCR_ROI_FWD", "cta")) {
       // (P = 7 with 32-channel items — half-warps taking x-bins 0-3 / 4-6, XB = 4, 6 CTAs/SM instead of 4 — was measured

@@ -325,6 +325,27 @@ def test_row_major_forward(ops, synth, oracle, tune, variant, K, mode, levels):
         assert not got[~live].any()
 
 
+def test_default_forward_dispatch(ops, synth, tune):
+    """Which forward kernel an unset LCR_ROI_FWD selects: the pipelined row-program kernel for the reference's pooler shape on
+    a serving batch (7x7, 256 channels, K >= 8 x SMs, >= 4 frames) — bit-identical to LCR_ROI_FWD=rmp —, the sample-walk warp
+    kernel otherwise (short lists, fewer frames) — bit-identical to LCR_ROI_FWD=warp."""
+    from gpu_util import N, T, nhwc
+    C, H, W = 256, 520, 704
+    for B, K, want in ((4, 2400, "rmp"), (2, 2400, "warp"), (4, 600, "warp")):
+        rois = synth.make_rois(K, 900 + K + B, img_h=H, img_w=W, mode="anchor", batch=B, edge_cases=True)
+        feat = nhwc(T(synth.make_features(B, C, H // 4, W // 4, seed=90 + B)))
+        out = {}
+        for v in (None, "rmp", "warp"):
+            tune(LCR_ROI_FWD=v)
+            canvas = torch.full((K, C, 7, 7), float("nan"), device="cuda:0")
+            out[v] = N(ops.roi_align_fwd([feat], [0.25], T(rois), None, (7, 7), 2, False, out=canvas))
+            assert np.isfinite(out[v]).all()
+        other = "warp" if want == "rmp" else "rmp"
+        assert np.array_equal(out[None], out[want]), (B, K, want)
+        assert not np.array_equal(out[None], out[other]), (B, K, "the two kernels round differently: the check above would be vacuous")
+        assert np.abs(out["rmp"] - out["warp"]).max() <= 2e-6 * np.abs(out["warp"]).max()
+
+
 @pytest.mark.parametrize("P", [7, 14])
 def test_default_coordinate_rule_reproduces_torchvision_cuda(ops, oracle, synth, P):
     """The library default rounds the sample coordinates as torchvision's CUDA kernel does (what the reference runs on a

@@ -7,7 +7,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
 echo "launch list rc=$?"
 # one timed step of the region kernels: 2 sub-batches x 7 matching launches; skip the eager step, the capture warm-up and the warm-up steps
 ncu --set full --clock-control none --import-source on \
-    -k regex:"roi_fwd_warp|paste_split|rpn_prefilter|rpn_sortfilter|nms_mask|nms_jacobi" -s 70 -c 14 \
+    -k regex:"roi_fwd_|paste_split|rpn_prefilter|rpn_sortfilter|nms_mask|nms_jacobi" -s 70 -c 14 \
     -f -o gpurun_out/prof_full $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out/

@@ -193,6 +193,90 @@ __global__ void __launch_bounds__(256) roi_bwd_generic_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Forward for maps the NHWC fast path does not take (NCHW as the reference's FPN emits them, any strides / pooled size /
+// sampling ratio): one CTA per (RoI, channel chunk) with the RoI's axis taps in shared memory.
+//
+// roi_fwd_generic_kernel recomputes the RoI geometry (5 loads, 4 divisions) and every sample's position and taps
+// (2 divisions + the clamping of axis_tap per sample and axis) in EVERY output thread: ~16 divisions per output element
+// next to its 16 loads.  Here the PH*gh + PW*gw taps of a RoI are computed once per CTA, by as many threads, and an
+// output element is 4 table reads per sample next to its loads.  Thread -> (channel, ph, pw) with pw fastest: the output
+// leaves as full lines, and on an NCHW map the lanes of a warp read neighbouring columns of the same few plane rows.
+// The arithmetic is the generic kernel's, operation for operation: results are bit-identical to it (and to the oracle's
+// restatement of the CPU op with LCR_ROI_CPU_COORDS).  RoIs with more than kPlaneTaps samples on an axis (adaptive
+// sampling_ratio on a huge RoI) compute their taps in place, like the generic kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPlaneTaps = 64;
+struct __align__(16) PlaneTap {
+  int lo, hi;  // lo < 0: the sample lies outside the map and contributes nothing
+  float w_lo, w_hi;
+};
+
+__device__ __forceinline__ PlaneTap plane_tap(float start, float bin, int grid, int size, int u, int cpu_coords) {
+  const int b = u / grid;
+  int lo, hi;
+  float wl, wh;
+  const bool ok = axis_tap(sample_pos(start, b, bin, u - b * grid, grid, cpu_coords), size, lo, hi, wl, wh);
+  return PlaneTap{ok ? lo : -1, hi, wl, wh};
+}
+
+// SR = 2: the reference's sampling ratio with the sample loops unrolled (4 samples, 16 loads in flight per output); SR = 0: any.
+template <int SR>
+__global__ void __launch_bounds__(256) roi_fwd_planes_kernel(const __grid_constant__ RoiParams p, float* __restrict__ out, int cchunk) {
+  __shared__ PlaneTap s_x[kPlaneTaps], s_y[kPlaneTaps];
+  const int chunks = (p.C + cchunk - 1) / cchunk;
+  const int k = (int)(blockIdx.x / (unsigned)chunks);
+  const int c0 = (int)(blockIdx.x - (unsigned)k * (unsigned)chunks) * cchunk;
+  const int nc = min(cchunk, p.C - c0);
+  const int PP = p.PH * p.PW;
+  const int total = nc * PP;
+  float* const o = out + ((size_t)k * p.C + c0) * PP;
+  const RoiGeom g = roi_geom(p, k);  // block-uniform
+  const int gh = SR ? SR : g.gh, gw = SR ? SR : g.gw;
+  if (!g.live || gh <= 0 || gw <= 0) {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) o[i] = 0.f;
+    return;
+  }
+  const LvParam& lv = p.lv[g.lvl];
+  const bool tabled = (long long)p.PH * gh <= kPlaneTaps && (long long)p.PW * gw <= kPlaneTaps;
+  if (tabled) {
+    const int ny = p.PH * gh, nx = p.PW * gw;
+    for (int t = threadIdx.x; t < ny + nx; t += blockDim.x) {
+      if (t < ny) s_y[t] = plane_tap(g.sh, g.bh, gh, lv.H, t, p.cpu_coords);
+      else s_x[t - ny] = plane_tap(g.sw, g.bw, gw, lv.W, t - ny, p.cpu_coords);
+    }
+    __syncthreads();
+  }
+  const int cnt = gh * gw;
+  const float count = (float)(cnt > 1 ? cnt : 1);
+  const float* const fb = lv.data + (size_t)g.b * lv.sn + (size_t)c0 * lv.sc;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int c = i / PP;
+    const int r = i - c * PP;
+    const int ph = r / p.PW, pw = r - ph * p.PW;
+    const float* const f = fb + (size_t)c * lv.sc;
+    float acc = 0.f;
+#pragma unroll
+    for (int iy = 0; iy < gh; ++iy) {
+      const PlaneTap ty = tabled ? s_y[ph * gh + iy] : plane_tap(g.sh, g.bh, gh, lv.H, ph * gh + iy, p.cpu_coords);
+      if (ty.lo < 0) continue;
+      const float* const r0 = f + ty.lo * lv.sh;
+      const float* const r1 = f + ty.hi * lv.sh;
+#pragma unroll
+      for (int ix = 0; ix < gw; ++ix) {
+        const PlaneTap tx = tabled ? s_x[pw * gw + ix] : plane_tap(g.sw, g.bw, gw, lv.W, pw * gw + ix, p.cpu_coords);
+        if (tx.lo < 0) continue;
+        float v = __fmul_rn(__fmul_rn(ty.w_lo, tx.w_lo), __ldg(r0 + tx.lo * lv.sw));
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(ty.w_lo, tx.w_hi), __ldg(r0 + tx.hi * lv.sw)));
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(ty.w_hi, tx.w_lo), __ldg(r1 + tx.lo * lv.sw)));
+        v = __fadd_rn(v, __fmul_rn(__fmul_rn(ty.w_hi, tx.w_hi), __ldg(r1 + tx.hi * lv.sw)));
+        acc = __fadd_rn(acc, v);
+      }
+    }
+    o[i] = __fdiv_rn(acc, count);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fast path (NHWC, sampling_ratio == 2, square P x P).
 // ------------------------------------------------------------------------------------------------
 enum : uint32_t { kSame = 0u, kShift = 1u, kNew = 2u, kModeMask = 3u, kBorder = 4u, kValid = 8u };
@@ -2504,6 +2588,19 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
     }
     if (PH == 7) return launch_fast<7, 128, false>(p, out, st);
     return launch_fast<14, 32, false>(p, out, st);
+  }
+  if (!tune_is("LCR_ROI_FWD", "generic") && (long long)PH * PW <= (1 << 20)) {
+    // per-RoI tap tables (roi_fwd_planes_kernel).  Channel chunk: the largest power of two that still gives `per_sm` CTAs
+    // per SM (short lists are latency-bound: more, shorter CTAs).
+    int per_sm = 8;
+    if (const char* v = tune_get("LCR_ROI_PLANES_CTAS")) per_sm = atoi(v) > 0 ? atoi(v) : per_sm;
+    int cchunk = 256;
+    while (cchunk > 8 && (long long)K * ((C + cchunk - 1) / cchunk) < (long long)per_sm * sm_count()) cchunk >>= 1;
+    const long long blocks = (long long)K * ((C + cchunk - 1) / cchunk);
+    LCR_REQUIRE(blocks < (1ll << 31) && (long long)cchunk * PH * PW < (1ll << 31), LCR_ERR_CAPACITY);
+    if (p.sr == 2) roi_fwd_planes_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(p, out, cchunk);
+    else roi_fwd_planes_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(p, out, cchunk);
+    return after_launch();
   }
   const size_t total = (size_t)K * C * PH * PW;
   const size_t want = (total + 255) / 256;

@@ -79,9 +79,11 @@ struct RoIAlignFn : public torch::autograd::Function<RoIAlignFn> {
     at::Tensor feat = input.scalar_type() == at::kFloat ? input : input.to(at::kFloat);
     if (!nhwc_dense(feat)) {
       feat = feat.contiguous();
-      // NCHW input: transposing the map once pays off when the pooled output outweighs it (the warp-item kernels
-      // gather whole channel vectors)
-      if (sr == 2 && PH == PW && (PH == 7 || PH == 14) && C % 4 == 0 && K * PH * PW >= N * H * W) {
+      // NCHW input: transposing the map once pays off above ~100 RoIs per 130x176 map (the warp-item kernels gather whole
+      // channel vectors; below that roi_fwd_planes_kernel pools the planes directly) — same rule as roi_align._prefer_nhwc,
+      // measured in profiles/r02c_roi_nchw_exp.jsonl
+      if (sr == 2 && PH == PW && (PH == 7 || PH == 14) && C % 4 == 0 &&
+          (double)K * PH * PW * C >= 8e5 + 0.08 * (double)N * C * H * W) {
         at::Tensor t = at::empty_strided({N, C, H, W}, {H * W * C, 1, W * C, C}, feat.options());
         check_rc(lcr_nchw_to_nhwc_f32(feat.data_ptr<float>(), t.data_ptr<float>(), (int)N, (int)C, (int)H, (int)W, current_stream()),
                  "nchw_to_nhwc");

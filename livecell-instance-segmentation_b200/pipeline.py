@@ -20,6 +20,7 @@ from typing import Callable, Optional, Tuple
 import torch
 
 from . import ops
+from .roi_align import _prefer_nhwc
 
 
 @dataclass
@@ -86,11 +87,12 @@ class RegionPipeline:
     # -- stage 2: RoIAlign ---------------------------------------------------------------------------
     def pool(self, features: torch.Tensor, rois: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """features: logical [B, C, h, w]; channels_last memory takes the fast path directly.  An NCHW map is transposed once
-        (tiled 16-byte transpose) when the pooled output outweighs it, otherwise pooled through its strides by the generic kernel."""
+        (tiled 16-byte transpose) when the list is long enough to pay for it (roi_align._prefer_nhwc), otherwise its planes are
+        pooled directly (roi_fwd_planes_kernel)."""
         c = self.cfg
         B, C, h, w = features.shape
         nhwc = features.stride() == (h * w * C, 1, w * C, C)
-        if not nhwc and C % 4 == 0 and rois.shape[0] * c.pooled_size * c.pooled_size >= B * h * w:
+        if not nhwc and C % 4 == 0 and _prefer_nhwc(features, rois.shape[0], c.pooled_size, c.pooled_size):
             features = ops.to_nhwc(features)
         return ops.roi_align_fwd([features], [c.spatial_scale], rois, None, (c.pooled_size, c.pooled_size), c.sampling_ratio, False,
                                  out=out)

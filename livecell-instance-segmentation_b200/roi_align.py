@@ -34,9 +34,13 @@ def _as_rois(rois) -> torch.Tensor:
 
 
 def _prefer_nhwc(x: torch.Tensor, K: int, PH: int, PW: int) -> bool:
-    """NCHW-contiguous input: transposing the map pays off once the pooled output outweighs it."""
+    """NCHW-contiguous input: transpose the map once (tiled 16-byte transpose) and pool with the NHWC warp-item kernels, or
+    pool the planes directly (roi_fwd_planes_kernel)?  Measured on B200 (profiles/r02c_roi_nchw_exp.jsonl, kernel time inside
+    a CUDA graph, 256 channels, 7x7): the planes kernel costs ~0.2 us per RoI (LSU-wavefront bound: a warp's 16 loads per
+    output each touch ~6 lines), the transpose ~15 us per 130x176 map plus the NHWC kernel's ~6 us floor: the direct kernel
+    wins below ~100 RoIs on a 130x176 map and ~70 on a 64x64 one.  In elements: pooled output >= 8e5 + 8 % of the map."""
     N, C, H, W = x.shape
-    return K * PH * PW >= N * H * W
+    return K * PH * PW * C >= 800_000 + 0.08 * N * C * H * W
 
 
 class _RoIAlignFn(torch.autograd.Function):

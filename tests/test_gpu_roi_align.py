@@ -384,3 +384,31 @@ def test_default_coordinate_rule_reproduces_torchvision_cuda(ops, oracle, synth,
         assert float((y - tv).abs().max()) <= 1e-6 * float(tv.abs().max())
     finally:
         o.set_roi_coord_rule(prev)
+
+
+@pytest.mark.parametrize("P,sr,al", [((7, 7), 2, False), ((14, 14), 2, True), ((5, 3), 3, False), ((7, 7), 0, False), ((2, 9), 0, True)])
+def test_planes_kernel_is_the_generic_kernel_bit_for_bit(ops, oracle, synth, tune, P, sr, al):
+    """Maps the NHWC fast path does not take (NCHW as the reference's FPN emits them; any pooled size / sampling ratio) are
+    pooled by roi_fwd_planes_kernel (per-RoI tap tables in shared memory, one CTA per RoI x channel chunk): same arithmetic
+    as the one-thread-per-output generic kernel (LCR_ROI_FWD=generic) -> identical bits, on one level and on a pyramid, with
+    short channel chunks (K small), dead / degenerate RoIs, and adaptive sampling grids wider than the table (in-place taps)."""
+    from gpu_util import N, T, assert_close_rel
+    C = 40
+    feats = [synth.make_features(2, C, 60, 72, seed=11), synth.make_features(2, C, 30, 36, seed=12)]
+    scales = [0.25, 0.125]
+    for K in (9, 700):
+        rois = synth.make_rois(K, 40 + K, img_h=240, img_w=288, batch=2, edge_cases=K >= 8)
+        rois[-1, 1:] = [1.0, 2.0, 287.0, 239.0]                      # adaptive grid: ceil(59 / 7) = 9 samples per bin > table
+        lvl = (np.arange(K) % 2).astype(np.int32)
+        lvl[-1] = 0
+        for fl, sc, lv in ((feats[:1], scales[:1], None), (feats, scales, T(lvl))):
+            got = ops.roi_align_fwd([T(f) for f in fl], sc, T(rois), lv, P, sr, al)
+            tune(LCR_ROI_FWD="generic")
+            ref = ops.roi_align_fwd([T(f) for f in fl], sc, T(rois), lv, P, sr, al)
+            tune(LCR_ROI_FWD=None)
+            assert torch.equal(got, ref)
+    # and against the oracle (one level, square pooling: the oracle's signature)
+    if P[0] == P[1]:
+        rois = synth.make_rois(64, 3, img_h=240, img_w=288, batch=2, edge_cases=True)
+        got = ops.roi_align_fwd([T(feats[0])], [0.25], T(rois), None, P, sr, al)
+        assert_close_rel(N(got), oracle.roi_align_fwd(feats[0], rois, P[0], P[1], 0.25, sr, al), RTOL)

@@ -624,7 +624,13 @@ def run_ours(args):
                     "api": f"pipeline.HostFedRegionPipeline.run (chunks of {args.chunk_frames} frames, H2D overlapped with compute)",
                     "d2h": "detection records + counts (pasted masks stay sharded in HBM, SURVEY §8e)",
                     "results_match_resident_run": e2e_ok, "host_cores_bound_to_gpu_numa_node": len(numa_cores), "numa_binding": numa_report},
-            "gpu_launches": int(launches), "launch_mode": launch_mode, "roofline": roofline, "kernels": kernels,
+            "gpu_launches": int(launches), "launch_mode": launch_mode, "roofline": roofline,
+            # the WHOLE step against the HBM roofline: the algorithmic bytes of all four stages (what `kernels` uses
+            # per stage) over the streamed step's device time — the stages overlap, so HBM is the one resource they all share
+            "step_roofline": {"bound": "hbm", "algorithmic_GB": sum(stage_bytes) / 1e9, "ms_per_step": ms_step,
+                              "achieved": sum(stage_bytes) / 1e9 / (ms_step * 1e-3), "peak": peak, "unit": "GB/s",
+                              "frac": sum(stage_bytes) / 1e9 / (ms_step * 1e-3) / peak},
+            "kernels": kernels,
             "streamed_counts_match_sequential_stages": seq_counts_match, "sustained": sustained,
             "nms_us_2000_boxes": nms_us if nms_us is not None else nms_us_eager, "nms_us_2000_boxes_eager": nms_us_eager,
             "proposals_per_frame": n_props / F, "detections_per_frame": n_det / F,

@@ -208,7 +208,10 @@ int lcr_level_map_f32(const float* boxes, int box_stride, int K, int k_min, int 
  * The warp-item fast paths (pooled tile assembled in shared memory and
  * written by one TMA bulk store; backward: bulk load + vector reductions) need sampling_ratio == 2, PH == PW in {7, 14},
  * sc == 1 (NHWC), C % 4 == 0, even sn / sh / sw, 8-byte aligned maps at least 4 columns wide and a 16-byte aligned
- * out / grad_out; every other configuration runs the generic kernels (same results).
+ * out / grad_out.  Every other configuration (NCHW maps as the reference's FPN emits them, any pooled size or sampling ratio)
+ * takes roi_fwd_planes_kernel forward — one CTA per (RoI, channel chunk), the RoI's axis taps in shared memory, the arithmetic
+ * of torchvision's per-output kernel operation for operation — and the per-output generic kernel backward (same results;
+ * LCR_ROI_FWD=generic selects the per-output forward kernel).
  * rois [K,5] = (batch_idx as float, x1, y1, x2, y2) (TV:ops/_utils.py:18-25).  A roi with batch_idx < 0, batch_idx >= N of
  * its level, or a roi_level outside [0, L) is padding: forward writes zeros for it, backward ignores it (no out-of-range
  * access).  roi_level [K] i32 or NULL (all rois on level 0).  out / grad_out: [K, C, PH, PW] contiguous.

@@ -249,21 +249,18 @@ __global__ void __launch_bounds__(256) roi_fwd_planes_kernel(const __grid_consta
   const int cnt = gh * gw;
   const float count = (float)(cnt > 1 ? cnt : 1);
   const float* const fb = lv.data + (size_t)g.b * lv.sn + (size_t)c0 * lv.sc;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int c = i / PP;
-    const int r = i - c * PP;
-    const int ph = r / p.PW, pw = r - ph * p.PW;
-    const float* const f = fb + (size_t)c * lv.sc;
+  // One output element: sum over the bin's gh x gw samples, in the order of torchvision's per-output kernel.
+  auto pool = [&](const float* __restrict__ f, int ph, int pw, auto&& ytap, auto&& xtap) -> float {
     float acc = 0.f;
 #pragma unroll
     for (int iy = 0; iy < gh; ++iy) {
-      const PlaneTap ty = tabled ? s_y[ph * gh + iy] : plane_tap(g.sh, g.bh, gh, lv.H, ph * gh + iy, p.cpu_coords);
+      const PlaneTap ty = ytap(ph * gh + iy, iy);
       if (ty.lo < 0) continue;
       const float* const r0 = f + ty.lo * lv.sh;
       const float* const r1 = f + ty.hi * lv.sh;
 #pragma unroll
       for (int ix = 0; ix < gw; ++ix) {
-        const PlaneTap tx = tabled ? s_x[pw * gw + ix] : plane_tap(g.sw, g.bw, gw, lv.W, pw * gw + ix, p.cpu_coords);
+        const PlaneTap tx = xtap(pw * gw + ix, ix);
         if (tx.lo < 0) continue;
         float v = __fmul_rn(__fmul_rn(ty.w_lo, tx.w_lo), __ldg(r0 + tx.lo * lv.sw));
         v = __fadd_rn(v, __fmul_rn(__fmul_rn(ty.w_lo, tx.w_hi), __ldg(r0 + tx.hi * lv.sw)));
@@ -272,7 +269,31 @@ __global__ void __launch_bounds__(256) roi_fwd_planes_kernel(const __grid_consta
         acc = __fadd_rn(acc, v);
       }
     }
-    o[i] = __fdiv_rn(acc, count);
+    return __fdiv_rn(acc, count);
+  };
+  if (SR > 0 && tabled && blockDim.x % PP == 0) {
+    // The launch made the block a multiple of PH*PW threads: a thread keeps ONE bin — its 2 + 2 taps live in registers —
+    // and walks the chunk's channels; the inner loop is 16 loads and their FMAs, no table reads and no index arithmetic
+    // (ncu of the table-reading loop, K = 1024: 15.9 M of its LSU wavefronts were the four LDS.128 per output).
+    const int bin = (int)threadIdx.x % PP, cstep = (int)blockDim.x / PP;
+    const int ph = bin / p.PW, pw = bin - ph * p.PW;
+    PlaneTap ty[SR > 0 ? SR : 1], tx[SR > 0 ? SR : 1];
+#pragma unroll
+    for (int j = 0; j < SR; ++j) {
+      ty[j] = s_y[ph * SR + j];
+      tx[j] = s_x[pw * SR + j];
+    }
+    for (int c = (int)threadIdx.x / PP; c < nc; c += cstep)
+      o[c * PP + bin] = pool(fb + (size_t)c * lv.sc, ph, pw, [&](int, int j) { return ty[j]; }, [&](int, int j) { return tx[j]; });
+    return;
+  }
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int c = i / PP;
+    const int r = i - c * PP;
+    const int ph = r / p.PW, pw = r - ph * p.PW;
+    o[i] = pool(fb + (size_t)c * lv.sc, ph, pw,
+                [&](int u, int) { return tabled ? s_y[u] : plane_tap(g.sh, g.bh, gh, lv.H, u, p.cpu_coords); },
+                [&](int u, int) { return tabled ? s_x[u] : plane_tap(g.sw, g.bw, gw, lv.W, u, p.cpu_coords); });
   }
 }
 
@@ -2590,16 +2611,22 @@ extern "C" int lcr_roi_align_fwd_f32(const LcrFeatLevel* levels_host, int L, int
     return launch_fast<14, 32, false>(p, out, st);
   }
   if (!tune_is("LCR_ROI_FWD", "generic") && (long long)PH * PW <= (1 << 20)) {
-    // per-RoI tap tables (roi_fwd_planes_kernel).  Channel chunk: the largest power of two that still gives `per_sm` CTAs
-    // per SM (short lists are latency-bound: more, shorter CTAs).
+    // per-RoI tap tables (roi_fwd_planes_kernel).  Block = a multiple of PH*PW threads where possible (one bin per thread, sr == 2);
+    // channel chunk = a whole number of passes of the block's channel lanes, the most passes that still give `per_sm` CTAs per SM
+    // (short lists are latency-bound: more, shorter CTAs).
+    const int pp = PH * PW;
+    const int threads = pp <= 256 ? (256 / pp) * pp : 256;
+    const int unit = pp <= 256 ? 256 / pp : 1;  // channels a block covers per pass
     int per_sm = 8;
     if (const char* v = tune_get("LCR_ROI_PLANES_CTAS")) per_sm = atoi(v) > 0 ? atoi(v) : per_sm;
-    int cchunk = 256;
-    while (cchunk > 8 && (long long)K * ((C + cchunk - 1) / cchunk) < (long long)per_sm * sm_count()) cchunk >>= 1;
+    int passes = (int)(((long long)K * C) / ((long long)unit * per_sm * sm_count()));
+    passes = passes < 1 ? 1 : passes;
+    int cchunk = unit * passes;
+    cchunk = cchunk > C ? C : (cchunk > 256 ? 256 / unit * unit : cchunk);
     const long long blocks = (long long)K * ((C + cchunk - 1) / cchunk);
     LCR_REQUIRE(blocks < (1ll << 31) && (long long)cchunk * PH * PW < (1ll << 31), LCR_ERR_CAPACITY);
-    if (p.sr == 2) roi_fwd_planes_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(p, out, cchunk);
-    else roi_fwd_planes_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(p, out, cchunk);
+    if (p.sr == 2) roi_fwd_planes_kernel<2><<<(unsigned)blocks, threads, 0, st>>>(p, out, cchunk);
+    else roi_fwd_planes_kernel<0><<<(unsigned)blocks, threads, 0, st>>>(p, out, cchunk);
     return after_launch();
   }
   const size_t total = (size_t)K * C * PH * PW;

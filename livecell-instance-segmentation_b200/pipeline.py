@@ -171,7 +171,12 @@ class StreamedRegionPipeline:
 
     All result buffers (masks, pooled features, records, counts) are owned by this object and reused by every batch — the
     reference allocates them per image (src/custom_maskrcnn.py:164-207).  ``capture()`` records every sub-batch's two stage
-    groups as CUDA graphs over static input buffers (`self.inputs`), after which ``run()`` only replays."""
+    groups as CUDA graphs over static input buffers (`self.inputs`), after which ``run()`` only replays.
+    ``nchw_features()`` adds a static NCHW-contiguous feature buffer (``self.inputs["feat_nchw"]``): when present, ``run()``
+    first transposes the batch's maps into the NHWC buffer on the caller's stream (one tiled-transpose launch, graphs or not)
+    — up front, where it still overlaps the previous batch's last paste.  Transposing each sub-batch's
+    maps inside its front group instead was measured slower (3.92 against 3.74 ms per 64 frames: the transpose is HBM-bound,
+    and so is the paste it would run beside)."""
 
     def __init__(self, cfg: RegionConfig, frames: int, feat_shape, image_size, num_anchors: int = 9, chunks: int = 2, device=None,
                  depth: int = 2):
@@ -209,6 +214,16 @@ class StreamedRegionPipeline:
         self._state = [None] * n_slots
         self._graphs = None
         self._batch = 0
+
+    def nchw_features(self, enable: bool = True) -> Optional[torch.Tensor]:
+        """Static NCHW-contiguous feature input [F, C, h, w] (None after disabling).  Graphs captured earlier keep their form:
+        capture() again after switching."""
+        if not enable:
+            self.inputs.pop("feat_nchw", None)
+            return None
+        if self.inputs.get("feat_nchw") is None:
+            self.inputs["feat_nchw"] = torch.empty(tuple(self.inputs["feat"].shape), dtype=torch.float32, device=self.device)
+        return self.inputs["feat_nchw"]
 
     # the two stage groups of one sub-batch ----------------------------------------------------------------------------
     def _front(self, c, inp, slot=None):
@@ -262,6 +277,8 @@ class StreamedRegionPipeline:
         main = torch.cuda.current_stream(self.device)
         base = (self._batch % self.depth) * self.chunks
         self._batch += 1
+        if inp.get("feat_nchw") is not None:     # NCHW-contiguous maps: one transpose of the batch into the NHWC buffer
+            ops.to_nhwc(inp["feat_nchw"], out=inp["feat"])   # (a plain launch; as a one-node graph it measured 0.3 ms slower per step)
         for c in range(self.chunks):
             slot = base + c
             if self.used[slot]:

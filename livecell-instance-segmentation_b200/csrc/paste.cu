@@ -509,7 +509,8 @@ extern "C" int lcr_paste_masks_u8(const float* probs, const float* boxes, const 
     int cap = 1;
     if (const char* v = tune_get("LCR_PASTE_CTAS")) cap = atoi(v);  // tuning switch
     if (cap >= 1 && cap < per_sm) per_sm = cap;
-    const long long max_blocks = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
+    long long max_blocks = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
+    if (const char* v = tune_get("LCR_PASTE_GRID")) max_blocks = atoi(v) > 0 ? atoi(v) : max_blocks;  // tuning switch: persistent CTAs in all
     const int blocks = (int)((long long)N < max_blocks ? N : max_blocks);
     kern<<<blocks, kSplitThreads, split_smem, as_stream(stream)>>>(probs, boxes, valid, N, M, H, W, threshold, (uint32_t)on_value, out,
                                                                   zb_bytes);

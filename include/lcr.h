@@ -295,6 +295,19 @@ int lcr_box_iou_f32(const float* boxes, int N, const float* gt, int G, float* io
 int lcr_box_iou_max_f32(const float* boxes, int N, const float* gt, int G, float* max_iou,
                         int64_t* argmax, void* stream);
 
+/* Fused matcher.  Replaces the five-op chain that follows box_iou at every training call site:
+ *   src/components/rpn.py:72-81      ious.max(dim=1); pos = max >= 0.5; neg = max < 0.3; pos.sum(); neg.sum()
+ *   src/custom_maskrcnn.py:221-225   ious.max(dim=1); labels[max_iou >= 0.4] = 1
+ *   src/custom_maskrcnn.py:249-251   foreground_mask = max_iou >= 0.4
+ * One kernel, no [N,G] matrix.  max_iou [N] f32 / argmax [N] i64 as lcr_box_iou_max_f32 (either may be NULL);
+ * pos_mask[i] = max_iou[i] >= pos_thr, neg_mask[i] = max_iou[i] < neg_thr, both [N] u8 (0/1; viewable as bool), compared in
+ * fp32 as ATen compares a float tensor with a scalar — a NaN row is in neither mask; counts [2] i32 (device) = the two
+ * population counts (zeroed by the call).  The random ± sub-sampling that follows (torch.randperm, rpn.py:84-98) stays with
+ * the caller for RNG parity.  G == 0 is LCR_ERR_INVALID_ARG: the reference returns its no-ground-truth loss before matching. */
+int lcr_match_boxes_f32(const float* boxes, int N, const float* gt, int G, float pos_thr, float neg_thr,
+                        float* max_iou, int64_t* argmax, uint8_t* pos_mask, uint8_t* neg_mask, int* counts,
+                        void* stream);
+
 /* Mask targets, batched.  Replaces the per-positive loop over extract_mask_target
  * (src/utils/mask_utils.py:6-46, :110-113): for target k, crop gt_masks[gt_index[k]] (uint8 [H,W]) to
  * the int-truncated, clipped box (x1 in [0,W-1], x2 in [x1+1,W], same for y) and resize bilinearly

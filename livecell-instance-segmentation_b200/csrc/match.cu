@@ -76,6 +76,66 @@ __global__ void __launch_bounds__(kIouThreads) iou_kernel(const float4* __restri
   }
 }
 
+// Fused anchor / proposal matcher: IoU row max + the two threshold masks + their population counts, one pass.
+// Follows src/components/rpn.py:72-81 (`pos_mask = max_ious >= 0.5; neg_mask = max_ious < 0.3; pos_mask.sum(); neg_mask.sum()`)
+// and src/custom_maskrcnn.py:221-225, 249-251 (`max_iou >= 0.4`): five ATen launches over an [N,G] matrix become one kernel
+// reading 16 B and writing 14 B per row box.  The row loop is iou_kernel<false>'s, statement for statement, so max / argmax
+// are the same bits; the comparisons are fp32 against fp32 thresholds (what ATen's compare-with-scalar does for a float
+// tensor); a NaN row (two zero-area boxes) is neither positive nor negative, as in the reference.
+__global__ void __launch_bounds__(kIouThreads) match_kernel(const float4* __restrict__ boxes, int N, const float4* __restrict__ gt, int G,
+                                                            float pos_thr, float neg_thr, float* __restrict__ max_out,
+                                                            long long* __restrict__ arg_out, uint8_t* __restrict__ pos_out,
+                                                            uint8_t* __restrict__ neg_out, int* __restrict__ counts) {
+  __shared__ float4 s_gt[kGtChunk];
+  __shared__ float s_area[kGtChunk];
+  __shared__ int s_cnt[2];
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  const int i = blockIdx.x * kIouThreads + threadIdx.x;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < N) a = __ldg(boxes + i);
+  const float area_a = box_area_tv(a);
+  float best = 0.f;
+  int best_j = 0;
+  bool best_nan = false, have = false;
+  for (int g0 = 0; g0 < G; g0 += kGtChunk) {
+    const int ng = min(kGtChunk, G - g0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < ng; j += kIouThreads) {
+      const float4 b = __ldg(gt + g0 + j);
+      s_gt[j] = b;
+      s_area[j] = box_area_tv(b);
+    }
+    __syncthreads();
+    if (i < N) {
+      for (int j = 0; j < ng; ++j) {
+        const float v = iou_tv(a, area_a, s_gt[j], s_area[j]);
+        if (!best_nan && (!have || v > best || v != v)) {
+          best = v;
+          best_j = g0 + j;
+          best_nan = (v != v);
+          have = true;
+        }
+      }
+    }
+  }
+  const bool pos = (i < N) && (best >= pos_thr);  // false for NaN
+  const bool neg = (i < N) && (best < neg_thr);
+  if (i < N) {
+    if (max_out) max_out[i] = best;
+    if (arg_out) arg_out[i] = (long long)best_j;
+    pos_out[i] = pos ? 1 : 0;
+    neg_out[i] = neg ? 1 : 0;
+  }
+  // counts: one ballot per warp, one shared add per warp, one global add per CTA and mask
+  const unsigned pb = __ballot_sync(0xffffffffu, pos), nb = __ballot_sync(0xffffffffu, neg);
+  if (lane_id() == 0) {
+    if (pb) atomicAdd(&s_cnt[0], __popc(pb));
+    if (nb) atomicAdd(&s_cnt[1], __popc(nb));
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
 // ATen upsample_bilinear2d source index (align_corners=False), see paste.cu / SURVEY App. B.4.
 __device__ __forceinline__ void src_index_mt(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
   float src = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);
@@ -233,6 +293,23 @@ extern "C" int lcr_box_iou_max_f32(const float* boxes, int N, const float* gt, i
   iou_kernel<false><<<(N + kIouThreads - 1) / kIouThreads, kIouThreads, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(boxes), N, reinterpret_cast<const float4*>(gt), G, nullptr, max_iou,
       reinterpret_cast<long long*>(argmax));
+  return after_launch();
+}
+
+extern "C" int lcr_match_boxes_f32(const float* boxes, int N, const float* gt, int G, float pos_thr, float neg_thr, float* max_iou,
+                                  int64_t* argmax, uint8_t* pos_mask, uint8_t* neg_mask, int* counts, void* stream) {
+  LCR_REQUIRE(N >= 0 && G > 0, LCR_ERR_INVALID_ARG);  // the reference returns its no-ground-truth loss before matching
+  LCR_REQUIRE(counts != nullptr, LCR_ERR_INVALID_ARG);
+  {
+    const int rc = cuda_status(cudaMemsetAsync(counts, 0, 2 * sizeof(int), as_stream(stream)));
+    if (rc != LCR_OK) return rc;
+  }
+  if (N == 0) return LCR_OK;
+  LCR_REQUIRE(boxes && gt && pos_mask && neg_mask, LCR_ERR_INVALID_ARG);
+  LCR_REQUIRE(aligned_to(boxes, 16) && aligned_to(gt, 16), LCR_ERR_ALIGNMENT);
+  match_kernel<<<(N + kIouThreads - 1) / kIouThreads, kIouThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(boxes), N, reinterpret_cast<const float4*>(gt), G, pos_thr, neg_thr, max_iou,
+      reinterpret_cast<long long*>(argmax), pos_mask, neg_mask, counts);
   return after_launch();
 }
 

@@ -512,6 +512,31 @@ def box_iou_max(boxes: torch.Tensor, gt: torch.Tensor):
     return mx, am
 
 
+def match_boxes(boxes: torch.Tensor, gt: torch.Tensor, pos_thr: float, neg_thr: Optional[float] = None):
+    """Fused matcher — `ious = box_iou(boxes, gt); max_iou, idx = ious.max(dim=1); pos = max_iou >= pos_thr;
+    neg = max_iou < neg_thr` plus the two `.sum()`s (src/components/rpn.py:72-81 with 0.5 / 0.3;
+    src/custom_maskrcnn.py:221-225, 249-251 with 0.4) in one kernel.  Returns (max_iou [N] f32, argmax [N] i64,
+    pos_mask [N] bool, neg_mask [N] bool, counts [2] i32 on the device: number of positives, number of negatives).
+    neg_thr=None: negatives are the complement threshold (`max_iou < pos_thr`), the box head's background."""
+    _need_cuda(boxes, gt)
+    a, b = _f32c(boxes).reshape(-1, 4), _f32c(gt).reshape(-1, 4)
+    N, G = a.shape[0], b.shape[0]
+    if G == 0:
+        raise _lib.LcrError("match_boxes: no ground-truth boxes (the reference returns its no-target loss before matching)")
+    if neg_thr is None:
+        neg_thr = pos_thr
+    mx = torch.empty((N,), dtype=torch.float32, device=a.device)
+    am = torch.empty((N,), dtype=torch.int64, device=a.device)
+    pos = torch.empty((N,), dtype=torch.uint8, device=a.device)
+    neg = torch.empty((N,), dtype=torch.uint8, device=a.device)
+    counts = torch.empty((2,), dtype=torch.int32, device=a.device)
+    with _dev(a.device):
+        check(_lib.load().lcr_match_boxes_f32(a.data_ptr(), N, b.data_ptr(), G, float(pos_thr), float(neg_thr), mx.data_ptr(),
+                                              am.data_ptr(), pos.data_ptr(), neg.data_ptr(), counts.data_ptr(), _stream()),
+              "match_boxes")
+    return mx, am, pos.view(torch.bool), neg.view(torch.bool), counts
+
+
 def mask_targets(gt_masks: torch.Tensor, boxes: torch.Tensor, gt_index: Optional[torch.Tensor] = None, mask_size: int = 28) -> torch.Tensor:
     """Batched extract_mask_target (src/utils/mask_utils.py:6-46): gt_masks [G,H,W] uint8, boxes [K,4],
     gt_index [K] i64 (None: mask k) -> [K,M,M] f32 bilinear crops."""

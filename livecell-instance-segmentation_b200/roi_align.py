@@ -195,6 +195,12 @@ def box_iou(boxes1: torch.Tensor, boxes2: torch.Tensor) -> torch.Tensor:
     return ops.box_iou(boxes1, boxes2)
 
 
+def match_boxes(boxes1: torch.Tensor, boxes2: torch.Tensor, pos_thr: float, neg_thr=None):
+    """``box_iou(boxes1, boxes2).max(dim=1)`` + ``>= pos_thr`` / ``< neg_thr`` masks + their sums, one kernel
+    (src/components/rpn.py:72-81, src/custom_maskrcnn.py:221-225): (max_iou, argmax, pos, neg, counts[2])."""
+    return ops.match_boxes(boxes1, boxes2, pos_thr, neg_thr)
+
+
 def box_iou_max(boxes1: torch.Tensor, boxes2: torch.Tensor):
     """(values, indices) of ``box_iou(boxes1, boxes2).max(dim=1)`` without materialising the matrix."""
     return ops.box_iou_max(boxes1, boxes2)

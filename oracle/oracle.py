@@ -324,6 +324,18 @@ def box_iou(boxes, gt, want_matrix=True):
     return iou, mx, am
 
 
+def match_boxes(boxes, gt, pos_thr, neg_thr=None):
+    """The threshold masks and their sums that follow the row max: src/components/rpn.py:76-81 (0.5 / 0.3),
+    src/custom_maskrcnn.py:224-225, 251 (0.4).  A float tensor compared with a Python scalar is compared in fp32 (ATen);
+    NaN rows fall in neither mask.  Returns (max [N] f32, argmax [N] i64, pos [N] bool, neg [N] bool, counts [2] i32)."""
+    _, mx, am = box_iou(boxes, gt, want_matrix=False)
+    neg_thr = pos_thr if neg_thr is None else neg_thr
+    with np.errstate(invalid="ignore"):
+        pos = mx >= np.float32(pos_thr)
+        neg = mx < np.float32(neg_thr)
+    return mx, am, pos, neg, np.array([pos.sum(), neg.sum()], np.int32)
+
+
 def mask_targets(gt_masks, boxes, gt_index=None, M=28) -> np.ndarray:
     """extract_mask_target (src/utils/mask_utils.py:6-46) for K (box, mask index) pairs."""
     m = np.ascontiguousarray(gt_masks, dtype=np.uint8)

@@ -42,6 +42,55 @@ def test_box_iou_full_size_vs_oracle_and_torchvision(ops, oracle, synth):
     assert int(pos.sum()) == int((torch.from_numpy(mx_ref) >= 0.5).sum()) and int(neg.sum()) == int((torch.from_numpy(mx_ref) < 0.3).sum())
 
 
+def test_match_boxes_golden_oracle_and_torchvision(ops, oracle, golden, synth):
+    """lcr_match_boxes_f32 — row max + threshold masks + sums in one kernel (src/components/rpn.py:72-81: 0.5 / 0.3;
+    src/custom_maskrcnn.py:221-225, 249-251: 0.4).  Bit-exact against (i) torch's own expressions on the reference-generated
+    row max of the golden fixture (NaN rows, a tie), (ii) the oracle at C1 size across two ground-truth chunks, (iii) the
+    reference's op chain run by torchvision / ATen on this GPU."""
+    import torchvision
+    from gpu_util import N, T
+    g = golden("match")
+    tmx = torch.from_numpy(g["max_iou"])
+    for pos_thr, neg_thr in ((0.5, 0.3), (0.4, None)):
+        mx, am, pos, neg, cnt = ops.match_boxes(T(g["boxes"]), T(g["gt"]), pos_thr, neg_thr)
+        assert pos.dtype == torch.bool and neg.dtype == torch.bool and cnt.dtype == torch.int32
+        assert np.array_equal(N(mx), g["max_iou"], equal_nan=True) and np.array_equal(N(am), g["argmax"])
+        t_pos, t_neg = tmx >= pos_thr, tmx < (pos_thr if neg_thr is None else neg_thr)
+        assert np.array_equal(N(pos), t_pos.numpy()) and np.array_equal(N(neg), t_neg.numpy())
+        assert cnt.tolist() == [int(t_pos.sum()), int(t_neg.sum())]
+    anc = ops.anchors(130, 176, 4, ops.base_anchors(), "cuda:0")
+    for G, seed in ((160, 3), (1500, 4)):
+        gt = synth.make_det_boxes(G, seed)
+        r_mx, r_am, r_pos, r_neg, r_cnt = oracle.match_boxes(N(anc), gt, 0.5, 0.3)
+        mx, am, pos, neg, cnt = ops.match_boxes(anc, T(gt), 0.5, 0.3)
+        assert np.array_equal(N(mx), r_mx, equal_nan=True) and np.array_equal(N(am), r_am)
+        assert np.array_equal(N(pos), r_pos) and np.array_equal(N(neg), r_neg) and cnt.tolist() == r_cnt.tolist()
+        assert 0 < r_cnt[0] < r_cnt[1] < anc.shape[0]                       # both masks populated, some anchors ignored
+        tv_mx, _ = torchvision.ops.box_iou(anc, T(gt)).max(dim=1)           # the chain the reference runs (rpn.py:72-77)
+        assert torch.equal(pos, tv_mx >= 0.5) and torch.equal(neg, tv_mx < 0.3)
+        assert cnt.tolist() == [int((tv_mx >= 0.5).sum().item()), int((tv_mx < 0.3).sum().item())]
+        # a second call on the same stream zeroes the counters itself
+        assert ops.match_boxes(anc, T(gt), 0.5, 0.3)[4].tolist() == r_cnt.tolist()
+    # a value exactly on a threshold: IoU of [0,0,2,2] with [0,0,2,1] is exactly 0.5 -> positive; 0.25 is < 0.3
+    b = T(np.array([[0, 0, 2, 1], [0, 0, 1, 1], [5, 5, 6, 6], [3, 3, 3, 3]], np.float32))
+    mx, am, pos, neg, cnt = ops.match_boxes(b, T(np.array([[0, 0, 2, 2], [3, 3, 3, 3]], np.float32)), 0.5, 0.3)
+    assert N(mx)[:3].tolist() == [0.5, 0.25, 0.0] and np.isnan(N(mx)[3])
+    assert N(pos).tolist() == [True, False, False, False] and N(neg).tolist() == [False, True, True, False]
+    assert cnt.tolist() == [1, 2]
+
+
+def test_match_boxes_edge_cases(ops):
+    from gpu_util import T
+    from livecell_instance_segmentation_b200._lib import LcrError
+    g = T(np.array([[0, 0, 1, 1]], np.float32))
+    mx, am, pos, neg, cnt = ops.match_boxes(T(np.zeros((0, 4), np.float32)), g, 0.5, 0.3)
+    assert mx.shape == (0,) and pos.shape == (0,) and cnt.tolist() == [0, 0]
+    with pytest.raises(LcrError):
+        ops.match_boxes(g, T(np.zeros((0, 4), np.float32)), 0.5, 0.3)   # no ground truth: the reference never matches
+    with pytest.raises(LcrError):
+        ops.match_boxes(g.cpu(), g.cpu(), 0.5)                          # CPU tensors: no fallback
+
+
 def test_box_iou_edge_cases(ops):
     from gpu_util import T
     from livecell_instance_segmentation_b200._lib import LcrError

@@ -176,6 +176,17 @@ def test_match_rows_golden(oracle, golden):
     assert np.isnan(g["max_iou"]).any() and (g["argmax"] == 2).any()   # the fixture exercises NaN rows and the tie
     _, mx2, am2 = oracle.box_iou(g["boxes"], g["gt"], want_matrix=False)
     assert np.array_equal(mx2, mx, equal_nan=True) and np.array_equal(am2, am)
+    # the threshold masks and sums that follow the row max (src/components/rpn.py:76-81, src/custom_maskrcnn.py:224-225),
+    # against the same expressions evaluated by torch on the reference's own row max
+    import torch
+    tmx = torch.from_numpy(g["max_iou"])
+    for pos_thr, neg_thr in ((0.5, 0.3), (0.4, None)):
+        mx3, am3, pos, neg, cnt = oracle.match_boxes(g["boxes"], g["gt"], pos_thr, neg_thr)
+        t_pos, t_neg = tmx >= pos_thr, tmx < (pos_thr if neg_thr is None else neg_thr)
+        assert np.array_equal(pos, t_pos.numpy()) and np.array_equal(neg, t_neg.numpy())
+        assert cnt.tolist() == [int(t_pos.sum().item()), int(t_neg.sum().item())]
+        assert not (pos | neg)[np.isnan(mx3)].any()                     # NaN rows are in neither mask
+        assert np.array_equal(mx3, mx, equal_nan=True) and np.array_equal(am3, am)
     tg = oracle.mask_targets(g["masks"], g["t_boxes"], g["t_index"], 28)
     assert tg.shape == g["targets"].shape
     # ATen's CPU bilinear kernel is FMA-contracted differently per build: values, not bits

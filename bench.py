@@ -609,6 +609,10 @@ def run_ours(args):
         extras["c2_train_shape"] = X.c2_train_shape(synth)
         extras["c2_train_shape_ms"] = extras["c2_train_shape"]["fwd_plus_bwd_ms"]
         extras.update(X.config_latency(ops, synth, RegionConfig, RegionPipeline))
+        try:
+            extras["match_boxes_c1"] = X.match_boxes_c1(ops, synth)
+        except Exception as exc:   # an extra, never the line
+            extras["match_boxes_c1"] = {"error": repr(exc)}
 
     if world > 1:
         dist.barrier()

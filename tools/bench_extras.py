@@ -5,6 +5,7 @@ CUDA events on the current stream and returns plain dicts.  Nothing here touches
     c5_sweep             BASELINE config C5: K x {1,4 levels} x {7,14} fwd + bwd, torchvision's sm_100 cubins beside it
     c2_train_shape       BASELINE config C2's RoIAlign: 128 RoIs on a 64x64 map, fwd + bwd through autograd
     config_latency       BASELINE configs C1 / C3: the whole region path of ONE frame as a CUDA graph
+    match_boxes_c1       f1: anchors x ground truth row max + threshold masks + sums, torchvision's chain beside it
     h2d_ceiling          plain cudaMemcpyAsync of the e2e step's inputs from pinned memory (what PCIe gives this rank)
 """
 import numpy as np
@@ -130,6 +131,29 @@ def c2_train_shape(synth, reps=20):
     tv = _timed(step(optv), reps, warm=5)
     return {"fwd_plus_bwd_ms": ours, "torchvision_cuda_fwd_plus_bwd_ms": tv, "K": 128, "map": "1x256x64x64 NCHW",
             "note": "launch-latency-bound (6.4 MB out, 4.2 MB grad map): both are ~40 us of kernels inside the autograd engine"}
+
+
+def match_boxes_c1(ops, synth, reps=20):
+    """f1 at BASELINE config C1 size: 205 920 anchors x 160 ground-truth boxes.  Ours = lcr_match_boxes_f32 (one kernel:
+    row max + `>= 0.5` / `< 0.3` masks + their sums); beside it the reference's chain as it runs on this GPU
+    (torchvision.ops.box_iou, .max(dim=1), two compares, two sums — src/components/rpn.py:72-81), results compared."""
+    import torch
+    import torchvision
+    dev = torch.device("cuda", torch.cuda.current_device())
+    anc = ops.anchors(130, 176, 4, ops.base_anchors(), dev)
+    gt = torch.from_numpy(synth.make_det_boxes(160, 3)).to(dev)
+
+    def tv_chain():
+        mx, _ = torchvision.ops.box_iou(anc, gt).max(dim=1)
+        pos, neg = mx >= 0.5, mx < 0.3
+        return pos, neg, pos.sum(), neg.sum()
+    ours = _timed(lambda: ops.match_boxes(anc, gt, 0.5, 0.3), reps, warm=5)
+    tv = _timed(tv_chain, reps, warm=5)
+    _, _, pos, neg, cnt = ops.match_boxes(anc, gt, 0.5, 0.3)
+    t_pos, t_neg, t_np, t_nn = tv_chain()
+    same = bool(torch.equal(pos, t_pos) and torch.equal(neg, t_neg) and cnt.tolist() == [int(t_np.item()), int(t_nn.item())])
+    return {"us": ours * 1e3, "torchvision_chain_us": tv * 1e3, "anchors": int(anc.shape[0]), "gt": 160,
+            "positives": int(cnt[0].item()), "negatives": int(cnt[1].item()), "equal_to_torchvision_chain": same}
 
 
 def config_latency(ops, synth, RegionConfig, RegionPipeline, reps=30):

@@ -114,10 +114,12 @@ def _forward_inference_batched(self, images):
                       mask_head=lambda rf: mask_head_probs(self.mask_head, rf))
 
 
-def install(import_missing: bool = True, batched_inference: bool = False) -> dict:
+def install(import_missing: bool = True, batched_inference: bool = False, fused_rpn_matching: bool = False) -> dict:
     """Patch every reference module that is (or can be) imported.  Returns {module: [patched names]}.
     batched_inference=True additionally swaps CustomMaskRCNN.forward_inference for the batched region pipeline
-    (_forward_inference_batched): same results, no per-image loop."""
+    (_forward_inference_batched): same results, no per-image loop.  fused_rpn_matching=True swaps RPN.compute_loss
+    (src/components/rpn.py:42-123) for matching.rpn_compute_loss: IoU matrix, row max, threshold masks and their sums in one
+    kernel, the same torch.randperm draws (same sample for the same generator state)."""
     done = {}
     targets = []                       # resolve (import) every module first, so that each one still binds the reference's own
     for mod_name, repl in PATCHES.items():   # callables when it is patched and uninstall() can give them back
@@ -136,6 +138,11 @@ def install(import_missing: bool = True, batched_inference: bool = False) -> dic
                 if getattr(mod, attr) is not obj:
                     _swap(mod, attr, obj)
                 done.setdefault(name, []).append(attr)
+        if fused_rpn_matching and name == "src.components.rpn" and hasattr(mod, "RPN"):
+            from .matching import rpn_compute_loss
+            if mod.RPN.compute_loss is not rpn_compute_loss:
+                _swap(mod.RPN, "compute_loss", rpn_compute_loss)
+            done.setdefault(name, []).append("RPN.compute_loss")
         if name.endswith("custom_maskrcnn") and hasattr(mod, "CustomMaskRCNN"):
             if mod.CustomMaskRCNN._generate_masks is not _paste_method:
                 _swap(mod.CustomMaskRCNN, "_generate_masks", _paste_method)

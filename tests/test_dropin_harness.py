@@ -53,3 +53,43 @@ def test_scripts_import_unchanged_with_stubs(tmp_path):
     assert status.startswith("Detected ") and len(shape) == 3
     preds, summary, _ = dc.run_tiles("cpu", False, tmp_path, n_tiles=1)
     assert preds[0]["masks"].dtype == np.uint8 and preds[0]["masks"].shape[1:] == (222, 300)
+
+
+def test_rpn_sampling_host_logic_draws_the_reference_sample_on_cpu(monkeypatch):
+    """matching.sample_rpn_anchors / rpn_compute_loss (the host logic above lcr_match_boxes_f32) against the reference's own
+    RPN.compute_loss (src/components/rpn.py:42-123) from the same generator state.  There is no GPU here, so the KERNEL is
+    stood in for by the oracle's match_boxes (test infrastructure; the product raises on CPU tensors —
+    tests/test_gpu_dropin.py::test_fused_rpn_matching_draws_the_reference_sample is the real comparison)."""
+    import importlib
+    import torch
+    from livecell_instance_segmentation_b200 import matching, ops
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import oracle
+
+    def stand_in(a, g, pos_thr, neg_thr=None):
+        mx, am, pos, neg, cnt = oracle.match_boxes(a.numpy(), g.numpy(), pos_thr, neg_thr)
+        return tuple(torch.from_numpy(np.ascontiguousarray(v)) for v in (mx, am, pos, neg, cnt))
+    with pytest.raises(Exception):
+        ops.match_boxes(torch.zeros((1, 4)), torch.zeros((1, 4)), 0.5)          # the product has no CPU path
+    monkeypatch.setattr(ops, "match_boxes", stand_in)
+    ref_harness.import_reference()
+    try:
+        rpn_mod = importlib.import_module("src.components.rpn")
+        anchors = importlib.import_module("src.components.anchor_generator").AnchorGenerator().generate_anchors((64, 64), stride=4, device="cpu")
+        rpn = rpn_mod.RPN(in_channels=8, num_anchors=9)
+        targets = dc.synth_targets(2, 256, 256, 5, "cpu")
+        scores = torch.randn((2, 9, 64, 64), generator=torch.Generator().manual_seed(3))
+
+        def run(fn, tg):
+            s = scores.clone().requires_grad_(True)
+            torch.manual_seed(77)
+            loss = fn(rpn, [s], [None], anchors, tg, "cpu")["loss_rpn_cls"]
+            loss.backward()
+            return loss.detach(), s.grad
+        (l_ref, g_ref), (l_got, g_got) = run(rpn_mod.RPN.compute_loss, targets), run(matching.rpn_compute_loss, targets)
+        assert torch.equal(l_ref, l_got) and torch.equal(g_ref, g_got)
+        assert int((g_ref != 0).sum()) == 256
+        empty = [{"boxes": torch.zeros((0, 4))} for _ in range(2)]
+        assert torch.equal(run(rpn_mod.RPN.compute_loss, empty)[0], run(matching.rpn_compute_loss, empty)[0])
+    finally:
+        ref_harness.purge()

@@ -183,3 +183,49 @@ def test_gradio_predict_and_tile_stitching_run_unchanged(tmp_path):
     for a, b in zip(ka, kp):
         assert a[0] == b[0] and a[1] == b[1] and abs(a[2] - b[2]) <= 1e-6 and abs(a[3] - b[3]) <= 2
     print(f"[dropin] gradio: {sp!r}; tiles: {sum(len(p['boxes']) for p in pp)} detections, {len(kp)} kept after border filtering")
+
+
+def test_fused_rpn_matching_draws_the_reference_sample():
+    """install(fused_rpn_matching=True): RPN.compute_loss (src/components/rpn.py:42-123) through lcr_match_boxes_f32.  The
+    reference's own method and the replacement are called on the same scores / anchors / targets from the same generator
+    state: same randperm draws -> the same ± sample -> the same loss and the same gradient, bit for bit; the branch without
+    ground truth and the restored method after uninstall() are checked too."""
+    from livecell_instance_segmentation_b200 import install as inst, matching, ops
+    ref_harness.import_reference()
+    import importlib
+    rpn_mod = importlib.import_module("src.components.rpn")
+    try:
+        original = rpn_mod.RPN.compute_loss
+        rpn = rpn_mod.RPN(in_channels=8, num_anchors=9).to(DEV)
+        B, H, W = 2, 64, 64
+        anchors = ops.anchors(H, W, 4, ops.base_anchors(), DEV)
+        targets = dc.synth_targets(B, 256, 256, 5, DEV)
+        g = torch.Generator(device=DEV).manual_seed(3)
+        scores = torch.randn((B, 9, H, W), generator=g, device=DEV)
+
+        def run(fn, tg):
+            s = scores.clone().requires_grad_(True)
+            torch.manual_seed(77)
+            loss = fn(rpn, [s], [None], anchors, tg, DEV)["loss_rpn_cls"]
+            loss.backward()
+            return loss.detach(), s.grad
+
+        l_ref, g_ref = run(original, targets)
+        l0 = _launches()
+        l_got, g_got = run(matching.rpn_compute_loss, targets)
+        assert _launches() > l0
+        assert torch.equal(l_ref, l_got) and torch.equal(g_ref, g_got), (float(l_ref), float(l_got))
+        assert int((g_ref != 0).sum()) == 256                                        # a full ± sample was drawn
+        torch.manual_seed(77)
+        sampled, labels, pos_s, neg_s = matching.sample_rpn_anchors(anchors, torch.cat([t["boxes"] for t in targets]))
+        assert len(sampled) == 256 and 0 < len(pos_s) <= 128 and float(labels.sum()) == len(pos_s)
+        assert torch.equal(torch.sort(sampled)[0], torch.nonzero(g_ref.permute(0, 2, 3, 1).reshape(-1))[:, 0])
+        empty = [{"boxes": torch.zeros((0, 4), device=DEV)} for _ in range(B)]
+        assert torch.equal(run(original, empty)[0], run(matching.rpn_compute_loss, empty)[0])   # no ground truth: 0.1
+        done = inst.install(fused_rpn_matching=True)
+        assert "RPN.compute_loss" in done["src.components.rpn"] and rpn_mod.RPN.compute_loss is matching.rpn_compute_loss
+        inst.uninstall()
+        assert rpn_mod.RPN.compute_loss is original
+    finally:
+        inst.uninstall()
+        ref_harness.purge()

@@ -43,12 +43,13 @@ def main():
         return
     dev = "cuda:0"
     res = {}
-    for patched in (False, True, "batched"):
+    for patched in (False, True, "batched", "fused"):
         cm = ref_harness.import_reference()
         if patched:
-            inst.install(batched_inference=(patched == "batched"))
+            inst.install(batched_inference=(patched == "batched"), fused_rpn_matching=(patched == "fused"))
         try:
-            tag = {False: "untouched", True: "patched", "batched": "patched_batched_inference"}[patched]
+            tag = {False: "untouched", True: "patched", "batched": "patched_batched_inference",
+                   "fused": "patched_fused_rpn_matching"}[patched]
             model = dc.new_model(cm, dev, 0).eval()
             imgs1 = torch.from_numpy(np.stack([dc.synth_image(520, 704, 150, 1)])).to(dev)
             dc.calibrate_rpn(model, imgs1)
@@ -82,6 +83,8 @@ def main():
     for k in ("inference_1x704x520_ms", "inference_8x704x520_ms", "train_step_8x256x256_ms"):
         res["speedup_" + k[:-3]] = res["untouched_" + k] / res["patched_" + k]
         res["speedup_batched_" + k[:-3]] = res["untouched_" + k] / res["patched_batched_inference_" + k]
+    res["speedup_fused_rpn_matching_train_step_8x256x256"] = (res["untouched_train_step_8x256x256_ms"]
+                                                              / res["patched_fused_rpn_matching_train_step_8x256x256_ms"])
     res["note"] = ("wall clock, device synchronised; same weights and inputs; the per-image Python loop of forward_inference, the backbone, FPN "
                    "and heads are the reference's own code in both arms")
     print(json.dumps(res), flush=True)

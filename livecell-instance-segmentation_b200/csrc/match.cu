@@ -82,6 +82,9 @@ __global__ void __launch_bounds__(kIouThreads) iou_kernel(const float4* __restri
 // reading 16 B and writing 14 B per row box.  The row loop is iou_kernel<false>'s, statement for statement, so max / argmax
 // are the same bits; the comparisons are fp32 against fp32 thresholds (what ATen's compare-with-scalar does for a float
 // tensor); a NaN row (two zero-area boxes) is neither positive nor negative, as in the reference.
+// Measured and dropped (profiles/r02d_match_ncu.md): a short path that skips iou_tv for pairs with an empty intersection and
+// a finite positive area sum (bit-identical on the hostile-input test) is SLOWER — 62 us against 52 us at C1 size: lanes of
+// a warp split between the two paths, and iou_tv's own `inter == 0` shortcut already keeps the division off the common path.
 __global__ void __launch_bounds__(kIouThreads) match_kernel(const float4* __restrict__ boxes, int N, const float4* __restrict__ gt, int G,
                                                             float pos_thr, float neg_thr, float* __restrict__ max_out,
                                                             long long* __restrict__ arg_out, uint8_t* __restrict__ pos_out,

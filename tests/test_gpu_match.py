@@ -79,6 +79,43 @@ def test_match_boxes_golden_oracle_and_torchvision(ops, oracle, golden, synth):
     assert cnt.tolist() == [1, 2]
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_match_boxes_short_path_is_exact_on_hostile_boxes(ops, oracle, seed):
+    """match_kernel skips the division for pairs with an empty intersection and a finite positive area sum; every other pair
+    (overlaps; zero, negative, overflowing or non-finite areas) takes iou_tv.  The result must be the bits of
+    lcr_box_iou_max_f32 (pinned to the golden row max) and of the oracle for malformed input too: inverted boxes (negative
+    areas -> -0 IoUs), zero-area boxes (0/0 = NaN), 1e38-sized and infinite coordinates, NaN coordinates, dense
+    overlaps, and a ground-truth list spanning two shared-memory chunks."""
+    from gpu_util import N, T
+    rng = np.random.RandomState(900 + seed)
+    n, g = 4000, (37, 1100, 300, 5)[seed]
+
+    def boxes(k, nonfinite):
+        x1, y1 = rng.uniform(-50, 400, k), rng.uniform(-50, 400, k)
+        b = np.stack([x1, y1, x1 + rng.uniform(0, 200, k), y1 + rng.uniform(0, 200, k)], 1).astype(np.float32)
+        kind = rng.randint(0, 12, k)
+        b[kind == 0, 2] = b[kind == 0, 0] - rng.uniform(1, 30, (kind == 0).sum())        # inverted in x: negative area
+        b[kind == 1, 3] = b[kind == 1, 1]                                                # zero height
+        b[kind == 2] = b[kind == 2][:, [0, 1, 0, 1]]                                     # a point: zero area
+        b[kind == 3, 2:] = b[kind == 3, :2] - 5.0                                        # inverted in both: positive area, empty
+        if nonfinite:
+            b[kind == 4] *= np.float32(1e36)                                             # areas overflow to inf
+            b[kind == 5, 2] = np.inf
+            b[kind == 6, 0] = -np.inf
+            b[kind == 7, rng.randint(0, 4)] = np.nan
+        return b
+    a, gt = boxes(n, seed >= 1), boxes(g, seed == 3)                # non-finite ground truth poisons every row: one small case only
+    with np.errstate(all="ignore"):
+        r_mx, r_am, r_pos, r_neg, r_cnt = oracle.match_boxes(a, gt, 0.5, 0.3)
+    k_mx, k_am = ops.box_iou_max(T(a), T(gt))
+    mx, am, pos, neg, cnt = ops.match_boxes(T(a), T(gt), 0.5, 0.3)
+    assert np.array_equal(N(mx).view(np.uint32), N(k_mx).view(np.uint32))       # bit for bit, -0 and NaN rows included
+    assert torch.equal(am, k_am)
+    assert np.array_equal(N(mx), r_mx, equal_nan=True) and np.array_equal(N(am), r_am)
+    assert np.array_equal(N(pos), r_pos) and np.array_equal(N(neg), r_neg) and cnt.tolist() == r_cnt.tolist()
+    assert np.isnan(N(mx)).any() and (seed == 3 or (np.isfinite(N(mx)) & (N(mx) > 0)).sum() > 1000)
+
+
 def test_match_boxes_edge_cases(ops):
     from gpu_util import T
     from livecell_instance_segmentation_b200._lib import LcrError

@@ -17,6 +17,15 @@ POS_IOU, NEG_IOU = 0.5, 0.3          # src/components/rpn.py:76-77
 MAX_POS, BATCH = 128, 256            # src/components/rpn.py:80-81
 
 
+def _draw(mask: torch.Tensor, n: int, device) -> torch.Tensor:
+    """n members of `mask` in the order of one torch.randperm over all of them (no draw at all for n == 0, as in
+    src/components/rpn.py:84-98, so the generator advances exactly as in the reference)."""
+    if n <= 0:
+        return torch.tensor([], dtype=torch.long, device=device)
+    members = torch.where(mask)[0]
+    return members[torch.randperm(len(members), device=device)[:n]]
+
+
 def sample_rpn_anchors(anchors: torch.Tensor, gt_boxes: torch.Tensor, pos_iou: float = POS_IOU, neg_iou: float = NEG_IOU,
                        max_pos: int = MAX_POS, batch: int = BATCH):
     """src/components/rpn.py:72-105.  Returns (sampled_indices [S] i64, labels [len(anchors)] f32 with 1.0 at the sampled
@@ -26,16 +35,8 @@ def sample_rpn_anchors(anchors: torch.Tensor, gt_boxes: torch.Tensor, pos_iou: f
     n_pos, n_neg = counts.tolist()                       # the one host sync (the reference: two .sum().item())
     num_pos = min(n_pos, max_pos)
     num_neg = min(n_neg, batch - num_pos)
-    if num_pos > 0:
-        pos_indices = torch.where(pos_mask)[0]
-        pos_sampled = pos_indices[torch.randperm(len(pos_indices), device=device)[:num_pos]]
-    else:
-        pos_sampled = torch.tensor([], dtype=torch.long, device=device)
-    if num_neg > 0:
-        neg_indices = torch.where(neg_mask)[0]
-        neg_sampled = neg_indices[torch.randperm(len(neg_indices), device=device)[:num_neg]]
-    else:
-        neg_sampled = torch.tensor([], dtype=torch.long, device=device)
+    pos_sampled = _draw(pos_mask, num_pos, device)       # positives first, then negatives: the reference's randperm order
+    neg_sampled = _draw(neg_mask, num_neg, device)
     labels = torch.zeros(len(anchors), dtype=torch.float32, device=device)
     labels[pos_sampled] = 1.0
     return torch.cat([pos_sampled, neg_sampled]), labels, pos_sampled, neg_sampled

@@ -93,3 +93,23 @@ def test_rpn_sampling_host_logic_draws_the_reference_sample_on_cpu(monkeypatch):
         assert torch.equal(run(rpn_mod.RPN.compute_loss, empty)[0], run(matching.rpn_compute_loss, empty)[0])
     finally:
         ref_harness.purge()
+
+
+def test_install_fused_rpn_matching_patches_and_restores_the_method():
+    """install(fused_rpn_matching=True) rebinds RPN.compute_loss of the staged reference and uninstall() gives it back; the
+    default install() leaves the method alone (patching only: nothing is launched on the CPU)."""
+    import importlib
+    from livecell_instance_segmentation_b200 import install as inst, matching
+    ref_harness.import_reference()
+    try:
+        rpn_mod = importlib.import_module("src.components.rpn")
+        original = rpn_mod.RPN.compute_loss
+        done = inst.install()
+        assert rpn_mod.RPN.compute_loss is original and "RPN.compute_loss" not in done.get("src.components.rpn", [])
+        inst.uninstall()
+        done = inst.install(fused_rpn_matching=True)
+        assert "RPN.compute_loss" in done["src.components.rpn"] and rpn_mod.RPN.compute_loss is matching.rpn_compute_loss
+        assert inst.uninstall() > 0 and rpn_mod.RPN.compute_loss is original
+    finally:
+        inst.uninstall()
+        ref_harness.purge()

@@ -81,9 +81,10 @@ def test_match_boxes_golden_oracle_and_torchvision(ops, oracle, golden, synth):
 
 @pytest.mark.parametrize("seed", range(4))
 def test_match_boxes_short_path_is_exact_on_hostile_boxes(ops, oracle, seed):
-    """match_kernel skips the division for pairs with an empty intersection and a finite positive area sum; every other pair
-    (overlaps; zero, negative, overflowing or non-finite areas) takes iou_tv.  The result must be the bits of
-    lcr_box_iou_max_f32 (pinned to the golden row max) and of the oracle for malformed input too: inverted boxes (negative
+    """Written for a short-path variant of match_kernel (no iou_tv for pairs with an empty intersection and a finite positive
+    area sum: bit-identical here, measured slower, reverted — profiles/r02d_match_ncu.md) and kept for the kernel in use:
+    the result must be the bits of lcr_box_iou_max_f32 (pinned to the golden row max) and of the oracle for malformed
+    input too: inverted boxes (negative
     areas -> -0 IoUs), zero-area boxes (0/0 = NaN), 1e38-sized and infinite coordinates, NaN coordinates, dense
     overlaps, and a ground-truth list spanning two shared-memory chunks."""
     from gpu_util import N, T

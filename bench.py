@@ -22,7 +22,8 @@ alone.  `e2e`: the same step through pipeline.HostFedRegionPipeline starting fro
 + D2H of the detection records inside the timed region), with the plain-memcpy ceiling of the same bytes beside it.
 Extras (N = 1): `roi_align_bwd` on the bench RoI list, `c5` (BASELINE config C5 sweep, torchvision's sm_100 cubins beside
 it), `c2_train_shape_ms`, `c1_latency_ms` / `c3_latency_ms`, `value_nchw_input` (NCHW feature maps, transpose inside the
-timed region), `sustained` (the step looped >= 3 s with the SM clock sampled).  N > 1: `multi_rank_check`.
+timed region), `sustained` (the step looped >= 3 s with the SM clock sampled), `match_boxes_c1` (the fused anchor matcher at
+C1 size, torchvision's chain beside it).  N > 1: `multi_rank_check`.
 `cpu_baseline` / `--impl reference`: the CPU oracle port (oracle/lcr_oracle.c, OpenMP over every usable host core — set
 explicitly, torchrun exports OMP_NUM_THREADS=1) on a bounded sample of the same workload; `cpu_baseline_reference_python`:
 the UNMODIFIED reference functions from the staged checkout baseline/_ref on the same host cores.
